@@ -5,5 +5,6 @@ Host side: Python/PyTorch mirror of the reference's model interface
 Import as ``eavqa_b200`` (see ``eavqa_b200.py`` at the repo root).
 """
 from . import synthetic  # noqa: F401
+from .model import ClipCaptionModelB200, ClipCaptionPrefixB200  # noqa: F401
 
-__all__ = ["synthetic"]
+__all__ = ["synthetic", "ClipCaptionModelB200", "ClipCaptionPrefixB200"]

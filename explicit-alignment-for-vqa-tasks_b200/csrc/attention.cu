@@ -1,0 +1,674 @@
+// Attention kernels of the CLIP-prefix LM step.
+//
+//  * lm_attention_{fwd,bwd}: GPT-2 causal attention with a key-padding mask (head_dim 64), flash
+//    style, 64x64 blocks, bf16 mma.sync.m16n8k16 with fp32 softmax statistics.  Sequences here are
+//    short (T = 50 in training, ~130 in few-shot prefill), so attention is <1% of the step's FLOPs
+//    (SURVEY.md 8d); it is latency/HBM-bound and written for that: one pass over q/k/v, nothing
+//    materialised in HBM but O and the log-sum-exp.
+//  * lm_attention_decode: one query per (batch, head) against the KV cache (HBM-bound streaming).
+//  * mapper_attention_{fwd,bwd}: the mapper's 8-head, unmasked self-attention over S = 20 rows
+//    (clipcap.py:81-104); fp32 CUDA-core math in shared memory.
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace eavqa {
+namespace {
+
+constexpr int HD = 64;        // GPT-2 head_dim
+constexpr int LDS = 72;       // smem row stride in bf16 (64 + 8 pad: conflict-free ldmatrix)
+constexpr int BLK = 64;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A fragment (16 rows x 16 k) of a row-major tile X[row][k]
+__device__ __forceinline__ void load_a(uint32_t (&a)[4], const bf16* tile, int row0, int k0, int lane) {
+    const int mi = lane >> 3, r = lane & 7;
+    ldmatrix_x4(a, smem_addr(tile + (row0 + (mi & 1) * 8 + r) * LDS + k0 + (mi >> 1) * 8));
+}
+// A fragment of X^T where X is stored [k][m]: rows m0.., contraction k0..
+__device__ __forceinline__ void load_a_trans(uint32_t (&a)[4], const bf16* tile, int m0, int k0, int lane) {
+    const int mi = lane >> 3, r = lane & 7;
+    ldmatrix_x4_trans(a, smem_addr(tile + (k0 + (mi >> 1) * 8 + r) * LDS + m0 + (mi & 1) * 8));
+}
+// B fragments for two adjacent n-tiles (n0, n0+8) from X[n][k] (contraction contiguous): b[0..1] tile 0, b[2..3] tile 1
+__device__ __forceinline__ void load_b(uint32_t (&b)[4], const bf16* tile, int n0, int k0, int lane) {
+    const int mi = lane >> 3, r = lane & 7;
+    ldmatrix_x4(b, smem_addr(tile + (n0 + (mi >> 1) * 8 + r) * LDS + k0 + (mi & 1) * 8));
+}
+// B fragments for two adjacent n-tiles from X[k][n] (contraction = stored rows)
+__device__ __forceinline__ void load_b_trans(uint32_t (&b)[4], const bf16* tile, int n0, int k0, int lane) {
+    const int mi = lane >> 3, r = lane & 7;
+    ldmatrix_x4_trans(b, smem_addr(tile + (k0 + (mi & 1) * 8 + r) * LDS + n0 + (mi >> 1) * 8));
+}
+
+// copy a 64 x 64 bf16 tile (rows row0.. of a [*, ld] matrix, 64 columns from col0) into smem; rows >= nrows -> 0
+__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t ld, int row0, int nrows, int tid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = tid + 128 * i;
+        const int r = idx >> 3, c = (idx & 7) * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (row0 + r < nrows) v = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(row0 + r) * ld + c);
+        *reinterpret_cast<uint4*>(dst + r * LDS + c) = v;
+    }
+}
+
+// S(16 x 64 per warp) = A(16 x 64, fragments af) * X[n][k]^T
+__device__ __forceinline__ void warp_gemm_nt(float (&acc)[8][4], const uint32_t (&af)[4][4], const bf16* xtile, int lane) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            load_b(b, xtile, np * 16, ks * 16, lane);
+            mma_bf16(acc[2 * np], af[ks], b[0], b[1]);
+            mma_bf16(acc[2 * np + 1], af[ks], b[2], b[3]);
+        }
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(128) lm_attention_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
+                                                               bf16* __restrict__ o, float* __restrict__ lse, int T,
+                                                               int H) {
+    __shared__ __align__(16) bf16 Qs[BLK * LDS];
+    __shared__ __align__(16) bf16 Ks[BLK * LDS];
+    __shared__ __align__(16) bf16 Vs[BLK * LDS];
+    __shared__ int kvalid[BLK];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int d = H * HD;
+    const int64_t ld = 3 * d;
+    const bf16* base = qkv + static_cast<int64_t>(b) * T * ld + h * HD;
+    const int q0 = qb * BLK;
+    const float scale = 0.125f;     // head_dim ** -0.5  (HF modeling_gpt2.py:96-98)
+
+    load_tile(Qs, base, ld, q0, T, tid);
+    __syncthreads();
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) load_a(qf[ks], Qs, warp * 16, ks * 16, lane);
+
+    float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
+    float oacc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oacc[i][e] = 0.f;
+
+    for (int kb = 0; kb <= qb; ++kb) {
+        const int k0 = kb * BLK;
+        __syncthreads();
+        load_tile(Ks, base + d, ld, k0, T, tid);
+        load_tile(Vs, base + 2 * d, ld, k0, T, tid);
+        if (tid < BLK) kvalid[tid] = (k0 + tid < T) ? valid[b * T + k0 + tid] : 0;
+        __syncthreads();
+
+        float sacc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sacc[i][e] = 0.f;
+        warp_gemm_nt(sacc, qf, Ks, lane);
+
+        float rmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = nt * 8 + 2 * t4 + (e & 1);
+                const int row = warp * 16 + g + ((e >> 1) << 3);
+                const bool ok = kvalid[col] && (k0 + col <= q0 + row);
+                const float s = ok ? sacc[nt][e] * scale : -INFINITY;
+                sacc[nt][e] = s;
+                rmax[e >> 1] = fmaxf(rmax[e >> 1], s);
+            }
+        float alpha[2], muse[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 1));
+            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 2));
+            const float mn = fmaxf(m_i[r], rmax[r]);
+            muse[r] = (mn == -INFINITY) ? 0.f : mn;
+            alpha[r] = __expf(m_i[r] - muse[r]);      // m_i = -inf -> 0
+            m_i[r] = mn;
+            l_i[r] *= alpha[r];
+        }
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float p0 = __expf(sacc[nt][0] - muse[0]), p1 = __expf(sacc[nt][1] - muse[0]);
+            const float p2 = __expf(sacc[nt][2] - muse[1]), p3 = __expf(sacc[nt][3] - muse[1]);
+            l_i[0] += p0 + p1;
+            l_i[1] += p2 + p3;
+            pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            oacc[i][0] *= alpha[0]; oacc[i][1] *= alpha[0];
+            oacc[i][2] *= alpha[1]; oacc[i][3] *= alpha[1];
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t bfr[4];
+                load_b_trans(bfr, Vs, np * 16, ks * 16, lane);
+                mma_bf16(oacc[2 * np], pf[ks], bfr[0], bfr[1]);
+                mma_bf16(oacc[2 * np + 1], pf[ks], bfr[2], bfr[3]);
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
+        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int qpos = q0 + warp * 16 + g + r * 8;
+        if (qpos >= T) continue;
+        const float inv = l_i[r] > 0.f ? 1.0f / l_i[r] : 0.f;
+        bf16* op = o + (static_cast<int64_t>(b) * T + qpos) * d + h * HD;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<uint32_t*>(op + nt * 8 + 2 * t4) = pack_bf16x2(oacc[nt][2 * r] * inv, oacc[nt][2 * r + 1] * inv);
+        if (lse != nullptr && t4 == 0)
+            lse[(static_cast<int64_t>(b) * H + h) * T + qpos] = (l_i[r] > 0.f) ? m_i[r] + logf(l_i[r]) : INFINITY;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// One CTA per (batch, head); outer loop over key blocks j, inner over query blocks i >= j.
+__global__ void __launch_bounds__(128) lm_attention_bwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
+                                                               const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                                                               const float* __restrict__ lse, bf16* __restrict__ dqkv,
+                                                               float* __restrict__ dq_scratch, int T, int H) {
+    extern __shared__ __align__(16) uint8_t smem_bwd[];
+    bf16* Qs = reinterpret_cast<bf16*>(smem_bwd);
+    bf16* Ks = Qs + BLK * LDS;
+    bf16* Vs = Ks + BLK * LDS;
+    bf16* dOs = Vs + BLK * LDS;
+    bf16* Ps = dOs + BLK * LDS;
+    bf16* dSs = Ps + BLK * LDS;
+    float* Ds = reinterpret_cast<float*>(dSs + BLK * LDS);
+    float* Ls = Ds + BLK;
+    int* kvalid = reinterpret_cast<int*>(Ls + BLK);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int d = H * HD;
+    const int64_t ld = 3 * d;
+    const bf16* base = qkv + static_cast<int64_t>(b) * T * ld + h * HD;
+    const bf16* obase = o + static_cast<int64_t>(b) * T * d + h * HD;
+    const bf16* dobase = d_o + static_cast<int64_t>(b) * T * d + h * HD;
+    bf16* dbase = dqkv + static_cast<int64_t>(b) * T * ld + h * HD;
+    float* dqs = dq_scratch ? dq_scratch + static_cast<int64_t>(b) * T * d + h * HD : nullptr;
+    const float scale = 0.125f;
+    const int nblk = (T + BLK - 1) / BLK;
+
+    for (int j = 0; j < nblk; ++j) {
+        const int k0 = j * BLK;
+        __syncthreads();
+        load_tile(Ks, base + d, ld, k0, T, tid);
+        load_tile(Vs, base + 2 * d, ld, k0, T, tid);
+        if (tid < BLK) kvalid[tid] = (k0 + tid < T) ? valid[b * T + k0 + tid] : 0;
+        float dkacc[8][4], dvacc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { dkacc[i][e] = 0.f; dvacc[i][e] = 0.f; }
+
+        for (int i = j; i < nblk; ++i) {
+            const int q0 = i * BLK;
+            __syncthreads();       // previous iteration's readers of Qs / dOs / Ps / dSs are done
+            load_tile(Qs, base, ld, q0, T, tid);
+            load_tile(dOs, dobase, d, q0, T, tid);
+            {   // D = rowsum(dO * O), lse: two threads per query row
+                const int r = tid >> 1, half = tid & 1;
+                float acc = 0.f;
+                if (q0 + r < T) {
+                    const uint4* op = reinterpret_cast<const uint4*>(obase + static_cast<int64_t>(q0 + r) * d + half * 32);
+                    const uint4* dp = reinterpret_cast<const uint4*>(dobase + static_cast<int64_t>(q0 + r) * d + half * 32);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 a = op[c], bb = dp[c];
+                        float2 x, y;
+                        x = unpack_bf16x2(a.x); y = unpack_bf16x2(bb.x); acc += x.x * y.x + x.y * y.y;
+                        x = unpack_bf16x2(a.y); y = unpack_bf16x2(bb.y); acc += x.x * y.x + x.y * y.y;
+                        x = unpack_bf16x2(a.z); y = unpack_bf16x2(bb.z); acc += x.x * y.x + x.y * y.y;
+                        x = unpack_bf16x2(a.w); y = unpack_bf16x2(bb.w); acc += x.x * y.x + x.y * y.y;
+                    }
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (half == 0) {
+                    Ds[r] = acc;
+                    Ls[r] = (q0 + r < T) ? lse[(static_cast<int64_t>(b) * H + h) * T + q0 + r] : 0.f;
+                }
+            }
+            __syncthreads();
+
+            uint32_t af[4][4];
+            float sacc[8][4], dpacc[8][4];
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { sacc[x][e] = 0.f; dpacc[x][e] = 0.f; }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) load_a(af[ks], Qs, warp * 16, ks * 16, lane);
+            warp_gemm_nt(sacc, af, Ks, lane);                      // S = Q K^T
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) load_a(af[ks], dOs, warp * 16, ks * 16, lane);
+            warp_gemm_nt(dpacc, af, Vs, lane);                     // dP = dO V^T
+
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float p[4], ds[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = nt * 8 + 2 * t4 + (e & 1);
+                    const int row = warp * 16 + g + ((e >> 1) << 3);
+                    const bool ok = kvalid[col] && (k0 + col <= q0 + row) && (q0 + row < T);
+                    p[e] = ok ? __expf(sacc[nt][e] * scale - Ls[row]) : 0.f;
+                    ds[e] = p[e] * (dpacc[nt][e] - Ds[row]);
+                }
+                const int r0 = warp * 16 + g, c0 = nt * 8 + 2 * t4;
+                *reinterpret_cast<uint32_t*>(Ps + r0 * LDS + c0) = pack_bf16x2(p[0], p[1]);
+                *reinterpret_cast<uint32_t*>(Ps + (r0 + 8) * LDS + c0) = pack_bf16x2(p[2], p[3]);
+                *reinterpret_cast<uint32_t*>(dSs + r0 * LDS + c0) = pack_bf16x2(ds[0], ds[1]);
+                *reinterpret_cast<uint32_t*>(dSs + (r0 + 8) * LDS + c0) = pack_bf16x2(ds[2], ds[3]);
+            }
+            __syncthreads();
+
+            // dV(keys 16w.. x hd) += P^T dO ;  dK += dS^T Q   (contraction over the 64 queries)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t pa[4], sa[4];
+                load_a_trans(pa, Ps, warp * 16, ks * 16, lane);
+                load_a_trans(sa, dSs, warp * 16, ks * 16, lane);
+#pragma unroll
+                for (int np = 0; np < 4; ++np) {
+                    uint32_t bfr[4];
+                    load_b_trans(bfr, dOs, np * 16, ks * 16, lane);
+                    mma_bf16(dvacc[2 * np], pa, bfr[0], bfr[1]);
+                    mma_bf16(dvacc[2 * np + 1], pa, bfr[2], bfr[3]);
+                    load_b_trans(bfr, Qs, np * 16, ks * 16, lane);
+                    mma_bf16(dkacc[2 * np], sa, bfr[0], bfr[1]);
+                    mma_bf16(dkacc[2 * np + 1], sa, bfr[2], bfr[3]);
+                }
+            }
+            // dQ(queries 16w.. x hd) = dS K   (contraction over the 64 keys)
+            float dqacc[8][4];
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dqacc[x][e] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t sa[4];
+                load_a(sa, dSs, warp * 16, ks * 16, lane);
+#pragma unroll
+                for (int np = 0; np < 4; ++np) {
+                    uint32_t bfr[4];
+                    load_b_trans(bfr, Ks, np * 16, ks * 16, lane);
+                    mma_bf16(dqacc[2 * np], sa, bfr[0], bfr[1]);
+                    mma_bf16(dqacc[2 * np + 1], sa, bfr[2], bfr[3]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int qpos = q0 + warp * 16 + g + r * 8;
+                if (qpos >= T) continue;
+                if (nblk == 1) {
+                    bf16* p = dbase + static_cast<int64_t>(qpos) * ld;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+                        *reinterpret_cast<uint32_t*>(p + nt * 8 + 2 * t4) =
+                            pack_bf16x2(dqacc[nt][2 * r] * scale, dqacc[nt][2 * r + 1] * scale);
+                } else {
+                    float* p = dqs + static_cast<int64_t>(qpos) * d;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        float2* q2 = reinterpret_cast<float2*>(p + nt * 8 + 2 * t4);
+                        float2 v = make_float2(dqacc[nt][2 * r] * scale, dqacc[nt][2 * r + 1] * scale);
+                        if (j > 0) {
+                            const float2 old = *q2;
+                            v.x += old.x;
+                            v.y += old.y;
+                        }
+                        *q2 = v;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int kpos = k0 + warp * 16 + g + r * 8;
+            if (kpos >= T) continue;
+            bf16* pk = dbase + static_cast<int64_t>(kpos) * ld + d;
+            bf16* pv = dbase + static_cast<int64_t>(kpos) * ld + 2 * d;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                *reinterpret_cast<uint32_t*>(pk + nt * 8 + 2 * t4) = pack_bf16x2(dkacc[nt][2 * r] * scale, dkacc[nt][2 * r + 1] * scale);
+                *reinterpret_cast<uint32_t*>(pv + nt * 8 + 2 * t4) = pack_bf16x2(dvacc[nt][2 * r], dvacc[nt][2 * r + 1]);
+            }
+        }
+    }
+    if (nblk > 1) {
+        __syncthreads();
+        for (int idx = tid; idx < T * (HD / 2); idx += blockDim.x) {
+            const int r = idx / (HD / 2), c = (idx % (HD / 2)) * 2;
+            const float2 v = *reinterpret_cast<const float2*>(dqs + static_cast<int64_t>(r) * d + c);
+            *reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r) * ld + c) = pack_bf16x2(v.x, v.y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ KV cache / decode
+__global__ void kv_cache_fill_kernel(const uint4* __restrict__ qkv, uint4* __restrict__ cache, int B, int T, int Tmax,
+                                     int d8) {
+    // per token row: copy the 2d bf16 (k | v) that follow the d query values
+    const int64_t total = static_cast<int64_t>(B) * T * 2 * d8;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % (2 * d8));
+        const int64_t row = i / (2 * d8);
+        const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
+        cache[(static_cast<int64_t>(b) * Tmax + t) * 2 * d8 + c] = qkv[row * 3 * d8 + d8 + c];
+    }
+}
+
+__global__ void __launch_bounds__(128) lm_attention_decode_kernel(const bf16* __restrict__ qkv_new, bf16* __restrict__ cache,
+                                                                  const int* __restrict__ valid, int valid_stride,
+                                                                  bf16* __restrict__ o, int B, int H, int pos, int Tmax) {
+    extern __shared__ float sc[];     // [4 warps][Tmax] scores
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x * 4 + warp;
+    if (bh >= B * H) return;
+    const int b = bh / H, h = bh % H;
+    const int d = H * HD;
+    float* s = sc + warp * Tmax;
+    const bf16* qrow = qkv_new + static_cast<int64_t>(b) * 3 * d + h * HD;
+    bf16* crow = cache + static_cast<int64_t>(b) * Tmax * 2 * d;
+    // append this step's k, v (2 elements per lane each)
+    {
+        const uint32_t kk = *reinterpret_cast<const uint32_t*>(qrow + d + 2 * lane);
+        const uint32_t vv = *reinterpret_cast<const uint32_t*>(qrow + 2 * d + 2 * lane);
+        *reinterpret_cast<uint32_t*>(crow + static_cast<int64_t>(pos) * 2 * d + h * HD + 2 * lane) = kk;
+        *reinterpret_cast<uint32_t*>(crow + static_cast<int64_t>(pos) * 2 * d + d + h * HD + 2 * lane) = vv;
+    }
+    __syncwarp();
+    float q[HD];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(qrow + c * 8);
+        float2 f;
+        f = unpack_bf16x2(u.x); q[c * 8 + 0] = f.x; q[c * 8 + 1] = f.y;
+        f = unpack_bf16x2(u.y); q[c * 8 + 2] = f.x; q[c * 8 + 3] = f.y;
+        f = unpack_bf16x2(u.z); q[c * 8 + 4] = f.x; q[c * 8 + 5] = f.y;
+        f = unpack_bf16x2(u.w); q[c * 8 + 6] = f.x; q[c * 8 + 7] = f.y;
+    }
+    const int n = pos + 1;
+    float mx = -INFINITY;
+    for (int t = lane; t < n; t += 32) {
+        float acc = -INFINITY;
+        if (valid[static_cast<int64_t>(b) * valid_stride + t]) {
+            const uint4* kp = reinterpret_cast<const uint4*>(crow + static_cast<int64_t>(t) * 2 * d + h * HD);
+            acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 u = kp[c];
+                float2 f;
+                f = unpack_bf16x2(u.x); acc += q[c * 8 + 0] * f.x + q[c * 8 + 1] * f.y;
+                f = unpack_bf16x2(u.y); acc += q[c * 8 + 2] * f.x + q[c * 8 + 3] * f.y;
+                f = unpack_bf16x2(u.z); acc += q[c * 8 + 4] * f.x + q[c * 8 + 5] * f.y;
+                f = unpack_bf16x2(u.w); acc += q[c * 8 + 6] * f.x + q[c * 8 + 7] * f.y;
+            }
+            acc *= 0.125f;
+        }
+        s[t] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    if (mx == -INFINITY) mx = 0.f;
+    float sum = 0.f;
+    for (int t = lane; t < n; t += 32) {
+        const float p = __expf(s[t] - mx);
+        s[t] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+    float a0 = 0.f, a1 = 0.f;
+    const bf16* vbase = crow + d + h * HD + 2 * lane;
+    for (int t = 0; t < n; ++t) {
+        const float p = s[t];
+        if (p != 0.f) {
+            const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vbase + static_cast<int64_t>(t) * 2 * d));
+            a0 += p * f.x;
+            a1 += p * f.y;
+        }
+    }
+    *reinterpret_cast<uint32_t*>(o + static_cast<int64_t>(b) * d + h * HD + 2 * lane) = pack_bf16x2(a0 * inv, a1 * inv);
+}
+
+// ------------------------------------------------------------------------------------------ mapper attention
+// smem (fp32): q, k, v [S][hd+1]  (+ do for backward), p [S][S+1] (+ dp)
+__global__ void __launch_bounds__(128) mapper_attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int S,
+                                                                   int H, int hd) {
+    extern __shared__ float sm[];
+    const int ldh = hd + 1, ldp = S + 1;
+    float* q = sm;
+    float* k = q + S * ldh;
+    float* v = k + S * ldh;
+    float* p = v + S * ldh;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int d = H * hd;
+    const bf16* base = qkv + static_cast<int64_t>(b) * S * 3 * d + h * hd;
+    for (int idx = threadIdx.x; idx < S * hd; idx += blockDim.x) {
+        const int i = idx / hd, c = idx % hd;
+        const bf16* row = base + static_cast<int64_t>(i) * 3 * d + c;
+        q[i * ldh + c] = __bfloat162float(row[0]);
+        k[i * ldh + c] = __bfloat162float(row[d]);
+        v[i * ldh + c] = __bfloat162float(row[2 * d]);
+    }
+    __syncthreads();
+    const float scale = rsqrtf(static_cast<float>(hd));      // clipcap.py:75
+    for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+        const int i = idx / S, j = idx % S;
+        float acc = 0.f;
+        for (int c = 0; c < hd; ++c) acc += q[i * ldh + c] * k[j * ldh + c];
+        p[i * ldp + j] = acc * scale;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < S; i += 4) {
+        float mx = -INFINITY;
+        for (int j = lane; j < S; j += 32) mx = fmaxf(mx, p[i * ldp + j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < S; j += 32) {
+            const float e = __expf(p[i * ldp + j] - mx);
+            p[i * ldp + j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = lane; j < S; j += 32) p[i * ldp + j] *= inv;
+    }
+    __syncthreads();
+    bf16* ob = o + static_cast<int64_t>(b) * S * d + h * hd;
+    for (int idx = threadIdx.x; idx < S * hd; idx += blockDim.x) {
+        const int i = idx / hd, c = idx % hd;
+        float acc = 0.f;
+        for (int j = 0; j < S; ++j) acc += p[i * ldp + j] * v[j * ldh + c];
+        ob[static_cast<int64_t>(i) * d + c] = __float2bfloat16(acc);
+    }
+}
+
+__global__ void __launch_bounds__(128) mapper_attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
+                                                                   bf16* __restrict__ dqkv, int S, int H, int hd) {
+    extern __shared__ float sm[];
+    const int ldh = hd + 1, ldp = S + 1;
+    float* q = sm;
+    float* k = q + S * ldh;
+    float* v = k + S * ldh;
+    float* go = v + S * ldh;
+    float* p = go + S * ldh;
+    float* ds = p + S * ldp;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int d = H * hd;
+    const bf16* base = qkv + static_cast<int64_t>(b) * S * 3 * d + h * hd;
+    const bf16* gbase = d_o + static_cast<int64_t>(b) * S * d + h * hd;
+    for (int idx = threadIdx.x; idx < S * hd; idx += blockDim.x) {
+        const int i = idx / hd, c = idx % hd;
+        const bf16* row = base + static_cast<int64_t>(i) * 3 * d + c;
+        q[i * ldh + c] = __bfloat162float(row[0]);
+        k[i * ldh + c] = __bfloat162float(row[d]);
+        v[i * ldh + c] = __bfloat162float(row[2 * d]);
+        go[i * ldh + c] = __bfloat162float(gbase[static_cast<int64_t>(i) * d + c]);
+    }
+    __syncthreads();
+    const float scale = rsqrtf(static_cast<float>(hd));
+    for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+        const int i = idx / S, j = idx % S;
+        float acc = 0.f, acc2 = 0.f;
+        for (int c = 0; c < hd; ++c) {
+            acc += q[i * ldh + c] * k[j * ldh + c];
+            acc2 += go[i * ldh + c] * v[j * ldh + c];
+        }
+        p[i * ldp + j] = acc * scale;
+        ds[i * ldp + j] = acc2;            // dP
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < S; i += 4) {
+        float mx = -INFINITY;
+        for (int j = lane; j < S; j += 32) mx = fmaxf(mx, p[i * ldp + j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < S; j += 32) {
+            const float e = __expf(p[i * ldp + j] - mx);
+            p[i * ldp + j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        float dot = 0.f;
+        for (int j = lane; j < S; j += 32) {
+            const float pv = p[i * ldp + j] * inv;
+            p[i * ldp + j] = pv;
+            dot += pv * ds[i * ldp + j];
+        }
+        dot = warp_sum(dot);
+        for (int j = lane; j < S; j += 32) ds[i * ldp + j] = p[i * ldp + j] * (ds[i * ldp + j] - dot) * scale;
+    }
+    __syncthreads();
+    bf16* dbase = dqkv + static_cast<int64_t>(b) * S * 3 * d + h * hd;
+    for (int idx = threadIdx.x; idx < S * hd; idx += blockDim.x) {
+        const int i = idx / hd, c = idx % hd;
+        float dq = 0.f, dk = 0.f, dv = 0.f;
+        for (int j = 0; j < S; ++j) {
+            dq += ds[i * ldp + j] * k[j * ldh + c];
+            dk += ds[j * ldp + i] * q[j * ldh + c];
+            dv += p[j * ldp + i] * go[j * ldh + c];
+        }
+        bf16* row = dbase + static_cast<int64_t>(i) * 3 * d + c;
+        row[0] = __float2bfloat16(dq);
+        row[d] = __float2bfloat16(dk);
+        row[2 * d] = __float2bfloat16(dv);
+    }
+}
+
+}  // namespace
+
+// ============================================================================================ launchers
+void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, int B, int T, int H, cudaStream_t s) {
+    dim3 grid(ceil_div(T, BLK), H, B);
+    lm_attention_fwd_kernel<<<grid, 128, 0, s>>>(qkv, valid, o, lse, T, H);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf16* d_o, const float* lse, bf16* dqkv,
+                      float* dq_scratch, int B, int T, int H, cudaStream_t s) {
+    const int smem = 6 * BLK * LDS * sizeof(bf16) + 2 * BLK * sizeof(float) + BLK * sizeof(int);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(lm_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    EAVQA_CHECK(T <= BLK || dq_scratch != nullptr, "lm_attention_bwd needs dq_scratch for T > 64");
+    dim3 grid(H, B);
+    lm_attention_bwd_kernel<<<grid, 128, smem, s>>>(qkv, valid, o, d_o, lse, dqkv, dq_scratch, T, H);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void kv_cache_fill(const bf16* qkv, bf16* cache, int B, int T, int Tmax, int d, cudaStream_t s) {
+    EAVQA_CHECK(d % 8 == 0, "kv cache width");
+    const int64_t total = static_cast<int64_t>(B) * T * 2 * (d / 8);
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 16));
+    kv_cache_fill_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(qkv), reinterpret_cast<uint4*>(cache), B, T,
+                                              Tmax, d / 8);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void lm_attention_decode(const bf16* qkv_new, bf16* cache, const int* valid, int valid_stride, bf16* o, int B, int H,
+                         int pos, int Tmax, cudaStream_t s) {
+    const int smem = 4 * Tmax * sizeof(float);
+    EAVQA_CHECK(smem <= 48 * 1024, "decode attention: sequence too long for the score buffer");
+    EAVQA_CHECK(pos < Tmax, "decode position beyond the KV cache");
+    lm_attention_decode_kernel<<<ceil_div(B * H, 4), 128, smem, s>>>(qkv_new, cache, valid, valid_stride, o, B, H, pos, Tmax);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void mapper_attention_fwd(const bf16* qkv, bf16* o, int B, int S, int H, int hd, cudaStream_t s) {
+    const int smem = (3 * S * (hd + 1) + S * (S + 1)) * sizeof(float);
+    EAVQA_CHECK(smem <= 200 * 1024, "mapper attention tile does not fit in shared memory");
+    static int configured = 0;
+    if (smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(mapper_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    dim3 grid(H, B);
+    mapper_attention_fwd_kernel<<<grid, 128, smem, s>>>(qkv, o, S, H, hd);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void mapper_attention_bwd(const bf16* qkv, const bf16* d_o, bf16* dqkv, int B, int S, int H, int hd, cudaStream_t s) {
+    const int smem = (4 * S * (hd + 1) + 2 * S * (S + 1)) * sizeof(float);
+    EAVQA_CHECK(smem <= 200 * 1024, "mapper attention tile does not fit in shared memory");
+    static int configured = 0;
+    if (smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(mapper_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    dim3 grid(H, B);
+    mapper_attention_bwd_kernel<<<grid, 128, smem, s>>>(qkv, d_o, dqkv, S, H, hd);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+}  // namespace eavqa

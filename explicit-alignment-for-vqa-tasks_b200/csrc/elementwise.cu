@@ -1,0 +1,630 @@
+// Fused, vectorised, coalesced memory-bound kernels of the CLIP-prefix LM step:
+// weight/activation packing (fp32->bf16, transpose, column sums), LayerNorm forward/backward,
+// embedding gather + prefix concat/splice + position add, LM-head cross-entropy bookkeeping,
+// greedy-decode argmax/EOS bookkeeping.  All are HBM/L2-bound: 16-byte accesses, warp-shuffle
+// reductions, no shared-memory round trips except the transpose tile and cross-warp reductions.
+#include <algorithm>
+#include <atomic>
+
+#include "kernels.cuh"
+
+namespace eavqa {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n); }
+int64_t kernel_launch_count() { return g_launches.load(); }
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ packing
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) convert_transpose_kernel(const T* __restrict__ src, int ld_src, int R, int C,
+                                                                bf16* __restrict__ dst, int ld_dst,
+                                                                bf16* __restrict__ dst_t, int ld_t,
+                                                                float* __restrict__ colsum) {
+    __shared__ float tile[32][33];
+    __shared__ float cs[8][32];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        float v = 0.f;
+        if (r < R && c < C) {
+            v = to_f32<T>(src[static_cast<size_t>(r) * ld_src + c]);
+            if (dst != nullptr) dst[static_cast<size_t>(r) * ld_dst + c] = __float2bfloat16(v);
+        }
+        tile[ty + 8 * i][tx] = v;
+        part += v;
+    }
+    if (colsum != nullptr) cs[ty][tx] = part;
+    __syncthreads();
+    if (colsum != nullptr && ty == 0 && c0 + tx < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += cs[i][tx];
+        atomicAdd(colsum + c0 + tx, s);
+    }
+    if (dst_t != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + ty + 8 * i, r = r0 + tx;
+            if (c < C && r < R) dst_t[static_cast<size_t>(c) * ld_t + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
+        }
+    }
+}
+
+__global__ void broadcast_rows_kernel(const float4* __restrict__ src, int n4, float4* __restrict__ dst,
+                                      int64_t batch_stride4, int B) {
+    const int64_t total = static_cast<int64_t>(B) * n4;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(i / n4), c = static_cast<int>(i % n4);
+        dst[b * batch_stride4 + c] = __ldg(src + c);
+    }
+}
+
+__global__ void sum_over_batch_kernel(const float* __restrict__ src, int64_t batch_stride, int B, int n,
+                                      float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += src[b * batch_stride + c];
+    out[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, int ld_x,
+                                                            const int* __restrict__ row_index,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, bf16* __restrict__ y,
+                                                            int ld_y, float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, int M, int d, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (m >= M) return;
+    const int xr = row_index ? row_index[m] : m;
+    const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(xr) * ld_x);
+    const int n4 = d >> 2;
+    float4 v[MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < n4) {
+            v[i] = xp[c];
+            sum += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    }
+    const float mean = warp_sum(sum) / d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < n4) {
+            const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+            sq += a * a + b * b + e * e + f * f;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / d + eps);
+    if (lane == 0) {
+        if (mean_out) mean_out[m] = mean;
+        if (rstd_out) rstd_out[m] = rstd;
+    }
+    uint2* yp = reinterpret_cast<uint2*>(y + static_cast<size_t>(m) * ld_y);
+    const float4* gp = reinterpret_cast<const float4*>(gamma);
+    const float4* bp = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < n4) {
+            const float4 g = __ldg(gp + c), b = __ldg(bp + c);
+            uint2 o;
+            o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+            o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+            yp[c] = o;
+        }
+    }
+}
+
+template <int MAXV, bool PARAM_GRADS>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, int ld_dy,
+                                                            const float* __restrict__ x, int ld_x,
+                                                            const int* __restrict__ row_index,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in, float* __restrict__ dx,
+                                                            int ld_dx, int accumulate, bf16* __restrict__ dx_bf16,
+                                                            int ld_dxb, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int M, int d) {
+    extern __shared__ float red[];   // PARAM_GRADS: [2][d] block-level dgamma / dbeta
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int n4 = d >> 2;
+    if (PARAM_GRADS) {
+        for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) red[i] = 0.f;
+        __syncthreads();
+    }
+    float4 ag[PARAM_GRADS ? MAXV : 1], ab[PARAM_GRADS ? MAXV : 1];
+    if (PARAM_GRADS) {
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const float4* gp = reinterpret_cast<const float4*>(gamma);
+    for (int m = blockIdx.x * wpb + warp; m < M; m += gridDim.x * wpb) {
+        const int xr = row_index ? row_index[m] : m;
+        const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(xr) * ld_x);
+        const uint2* dyp = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(m) * ld_dy);
+        const float mean = mean_in[m], rstd = rstd_in[m];
+        float4 xh[MAXV], g[MAXV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < n4) {
+                const float4 xv = xp[c];
+                const uint2 u = dyp[c];
+                const float2 d0 = unpack_bf16x2(u.x), d1 = unpack_bf16x2(u.y);
+                const float4 gm = __ldg(gp + c);
+                xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+                if (PARAM_GRADS) {
+                    ag[i].x += d0.x * xh[i].x; ag[i].y += d0.y * xh[i].y; ag[i].z += d1.x * xh[i].z; ag[i].w += d1.y * xh[i].w;
+                    ab[i].x += d0.x; ab[i].y += d0.y; ab[i].z += d1.x; ab[i].w += d1.y;
+                }
+                g[i] = make_float4(d0.x * gm.x, d0.y * gm.y, d1.x * gm.z, d1.y * gm.w);
+                s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+                s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+            }
+        }
+        s1 = warp_sum(s1) / d;
+        s2 = warp_sum(s2) / d;
+        float4* dxp = reinterpret_cast<float4*>(dx + static_cast<size_t>(xr) * ld_dx);
+        uint2* dbp = dx_bf16 ? reinterpret_cast<uint2*>(dx_bf16 + static_cast<size_t>(xr) * ld_dxb) : nullptr;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < n4) {
+                float4 r;
+                r.x = rstd * (g[i].x - s1 - xh[i].x * s2);
+                r.y = rstd * (g[i].y - s1 - xh[i].y * s2);
+                r.z = rstd * (g[i].z - s1 - xh[i].z * s2);
+                r.w = rstd * (g[i].w - s1 - xh[i].w * s2);
+                if (accumulate) {
+                    const float4 o = dxp[c];
+                    r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+                }
+                dxp[c] = r;
+                if (dbp) {
+                    uint2 o;
+                    o.x = pack_bf16x2(r.x, r.y);
+                    o.y = pack_bf16x2(r.z, r.w);
+                    dbp[c] = o;
+                }
+            }
+        }
+    }
+    if (PARAM_GRADS) {
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < n4) {
+                atomicAdd(red + 4 * c + 0, ag[i].x); atomicAdd(red + 4 * c + 1, ag[i].y);
+                atomicAdd(red + 4 * c + 2, ag[i].z); atomicAdd(red + 4 * c + 3, ag[i].w);
+                atomicAdd(red + d + 4 * c + 0, ab[i].x); atomicAdd(red + d + 4 * c + 1, ab[i].y);
+                atomicAdd(red + d + 4 * c + 2, ab[i].z); atomicAdd(red + d + 4 * c + 3, ab[i].w);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < d; i += blockDim.x) {
+            atomicAdd(dgamma + i, red[i]);
+            atomicAdd(dbeta + i, red[d + i]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ embedding / splice
+__global__ void prepend_plan_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ mask, int B, int Tt,
+                                    int P, int* __restrict__ plan, int* __restrict__ valid) {
+    const int T = P + Tt;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    const int b = i / T, t = i % T;
+    if (t < P) {
+        plan[i] = -(t + 1);
+        valid[i] = 1;
+    } else {
+        plan[i] = static_cast<int>(tokens[b * Tt + t - P]);
+        valid[i] = mask ? (mask[b * Tt + t - P] != 0) : 1;
+    }
+}
+
+// one warp per prompt row: ballot prefix-sum of sentinel flags -> destination index of every text
+// token and every prefix row (vct0.py:494-533: dest = (j - c) + P * c).
+__global__ void splice_plan_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ mask, int B, int Tt,
+                                   int P, int n_img, int64_t sent_lo, int64_t sent_hi, int* __restrict__ plan,
+                                   int* __restrict__ valid, int* __restrict__ err_flag) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const int b = warp;
+    const int T_out = Tt + (P - 1) * n_img;
+    int base = 0;
+    for (int j0 = 0; j0 < Tt; j0 += 32) {
+        const int j = j0 + lane;
+        int64_t tok = 0;
+        bool sent = false;
+        if (j < Tt) {
+            tok = tokens[b * Tt + j];
+            sent = tok >= sent_lo && tok <= sent_hi;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, sent);
+        const int c = base + __popc(bal & ((1u << lane) - 1u));
+        if (j < Tt) {
+            const int dst = (j - c) + P * c;
+            if (sent) {
+                if (c < n_img)
+                    for (int r = 0; r < P; ++r)
+                        if (dst + r < T_out) {
+                            plan[b * T_out + dst + r] = -(c * P + r + 1);
+                            valid[b * T_out + dst + r] = 1;
+                        }
+            } else if (dst < T_out) {
+                plan[b * T_out + dst] = static_cast<int>(tok);
+                valid[b * T_out + dst] = mask ? (mask[b * Tt + j] != 0) : 1;
+            }
+        }
+        base += __popc(bal);
+    }
+    if (lane == 0 && base != n_img) atomicExch(err_flag, 1);
+}
+
+__global__ void __launch_bounds__(256) embed_rows_kernel(const int* __restrict__ plan, int rows, int T, int d,
+                                                         const float* __restrict__ wte, int vocab,
+                                                         const float* __restrict__ prefix, int64_t prefix_batch_stride,
+                                                         int prefix_row_stride, const float* __restrict__ wpe,
+                                                         float* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= rows) return;
+    const int b = row / T, t = row % T;
+    const int p = plan[row];
+    const float4* src;
+    if (p >= 0) {
+        const int tok = p < vocab ? p : vocab - 1;
+        src = reinterpret_cast<const float4*>(wte + static_cast<size_t>(tok) * d);
+    } else {
+        src = reinterpret_cast<const float4*>(prefix + b * prefix_batch_stride + static_cast<size_t>(-p - 1) * prefix_row_stride);
+    }
+    const float4* pe = wpe ? reinterpret_cast<const float4*>(wpe + static_cast<size_t>(t) * d) : nullptr;
+    float4* o = reinterpret_cast<float4*>(out + static_cast<size_t>(row) * d);
+    for (int c = lane; c < (d >> 2); c += 32) {
+        float4 v = __ldg(src + c);
+        if (pe) {
+            const float4 w = __ldg(pe + c);
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        o[c] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ cross-entropy
+__global__ void ce_plan_kernel(const int64_t* __restrict__ labels, int B, int Tt, int T, int P, int vocab,
+                               int* __restrict__ row_index, int* __restrict__ label, int* __restrict__ n_valid) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (r < B * Tt) {
+        const int b = r / Tt, j = r % Tt;
+        const int64_t lab = labels[r];
+        ok = lab >= 0 && lab < vocab;        // -100 = ignore_index
+        row_index[r] = b * T + P - 1 + j;
+        label[r] = ok ? static_cast<int>(lab) : -1;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_valid, __popc(bal));
+}
+
+__global__ void __launch_bounds__(256) ce_finalize_kernel(const float2* __restrict__ partial, int tiles,
+                                                          const float* __restrict__ target,
+                                                          const int* __restrict__ label, float* __restrict__ lse,
+                                                          float* __restrict__ loss_sum, int M) {
+    __shared__ float block_loss[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    float row_loss = 0.f;
+    if (r < M) {
+        float m = -INFINITY, s = 0.f;
+        for (int i = lane; i < tiles; i += 32) {
+            const float2 p = partial[static_cast<size_t>(r) * tiles + i];
+            if (p.x > -INFINITY) {
+                const float nm = fmaxf(m, p.x);
+                s = s * __expf(m - nm) + p.y * __expf(p.x - nm);
+                m = nm;
+            }
+        }
+        const float gm = warp_max(m);
+        s = (m > -INFINITY) ? s * __expf(m - gm) : 0.f;
+        s = warp_sum(s);
+        const float l = gm + logf(s);
+        if (lane == 0) {
+            lse[r] = l;
+            if (label[r] >= 0) row_loss = l - target[r];
+        }
+    }
+    if (lane == 0) block_loss[warp] = row_loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += block_loss[i];
+        if (t != 0.f) atomicAdd(loss_sum, t);
+    }
+}
+
+__global__ void ce_loss_kernel(const float* loss_sum, const int* n_valid, float* loss_out) {
+    *loss_out = *loss_sum / static_cast<float>(*n_valid);    // 0/0 = NaN, like the mean over no targets
+}
+
+__global__ void __launch_bounds__(256) ce_dlogits_kernel(bf16* __restrict__ z, int ld, int vocab, int n_cols,
+                                                         const float* __restrict__ lse, const int* __restrict__ label,
+                                                         const int* __restrict__ n_valid) {
+    const int r = blockIdx.x;
+    const int lab = label[r];
+    uint4* zp = reinterpret_cast<uint4*>(z + static_cast<size_t>(r) * ld);
+    const int n8 = n_cols >> 3;
+    if (lab < 0) {
+        for (int c = threadIdx.x; c < n8; c += blockDim.x) zp[c] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const float l = lse[r];
+    const float w = 1.0f / static_cast<float>(*n_valid);
+    for (int c = threadIdx.x; c < n8; c += blockDim.x) {
+        const uint4 u = zp[c];
+        float f[8];
+        float2 t;
+        t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+        t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+        t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+        t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+        const int v0 = c * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int v = v0 + k;
+            float g = 0.f;
+            if (v < vocab) {
+                g = __expf(f[k] - l);
+                if (v == lab) g -= 1.0f;
+                g *= w;
+            }
+            f[k] = g;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+        zp[c] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ greedy decode
+__global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restrict__ logits, int ld, int vocab, int step,
+                                                          int max_new, int has_eos, int64_t pad_id, int64_t eos_id,
+                                                          int* __restrict__ unfinished,
+                                                          int64_t* __restrict__ tokens_out,
+                                                          int* __restrict__ n_unfinished,
+                                                          float* __restrict__ top_logit,
+                                                          const float* __restrict__ wte,
+                                                          const float* __restrict__ wpe_row, int d,
+                                                          float* __restrict__ x_next, int* __restrict__ valid_next,
+                                                          int valid_stride) {
+    __shared__ float s_val[8];
+    __shared__ int s_idx[8];
+    __shared__ int s_next;
+    const int b = blockIdx.x;
+    const float* lp = logits + static_cast<size_t>(b) * ld;
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+    for (int v = threadIdx.x; v < vocab; v += blockDim.x) {
+        const float x = lp[v];
+        if (x > best) {          // strided scan visits increasing v: first maximum wins within a thread
+            best = x;
+            best_i = v;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) {
+            best = ov;
+            best_i = oi;
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        s_val[warp] = best;
+        s_idx[warp] = best_i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i)
+            if (s_val[i] > best || (s_val[i] == best && s_idx[i] < best_i)) {
+                best = s_val[i];
+                best_i = s_idx[i];
+            }
+        if (best_i == 0x7fffffff) best_i = 0;
+        int unf = unfinished[b];
+        int64_t out = best_i;
+        if (has_eos) {
+            out = unf ? static_cast<int64_t>(best_i) : pad_id;      // clipcap.py:431-434
+            unf = unf && (out != eos_id);                           // clipcap.py:458-461
+        }
+        tokens_out[static_cast<size_t>(b) * max_new + step] = out;
+        unfinished[b] = unf;
+        if (unf) atomicAdd(n_unfinished + step, 1);
+        if (top_logit) top_logit[static_cast<size_t>(b) * max_new + step] = best;
+        if (valid_next) valid_next[static_cast<size_t>(b) * valid_stride] = 1;   // appended position attends as 1
+        s_next = best_i;                                            // the RAW argmax is fed back (clipcap.py:423)
+    }
+    __syncthreads();
+    const float4* e = reinterpret_cast<const float4*>(wte + static_cast<size_t>(s_next) * d);
+    const float4* pe = reinterpret_cast<const float4*>(wpe_row);
+    float4* o = reinterpret_cast<float4*>(x_next + static_cast<size_t>(b) * d);
+    for (int c = threadIdx.x; c < (d >> 2); c += blockDim.x) {
+        float4 v = __ldg(e + c);
+        const float4 w = __ldg(pe + c);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        o[c] = v;
+    }
+}
+
+}  // namespace
+
+// ============================================================================================ launchers
+void convert_transpose_f32(const float* src, int ld_src, int R, int C, bf16* dst, int ld_dst, bf16* dst_t, int ld_t,
+                           float* colsum, cudaStream_t s) {
+    dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);
+    convert_transpose_kernel<float><<<grid, block, 0, s>>>(src, ld_src, R, C, dst, ld_dst, dst_t, ld_t, colsum);
+    KERNEL_CHECK();
+    count_launch();
+}
+void convert_transpose_bf16(const bf16* src, int ld_src, int R, int C, bf16* dst_t, int ld_t, float* colsum,
+                            cudaStream_t s) {
+    dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);
+    convert_transpose_kernel<bf16><<<grid, block, 0, s>>>(src, ld_src, R, C, nullptr, 0, dst_t, ld_t, colsum);
+    KERNEL_CHECK();
+    count_launch();
+}
+void broadcast_rows_f32(const float* src, int rows, int d, float* dst, int64_t batch_stride, int B, cudaStream_t s) {
+    EAVQA_CHECK(d % 4 == 0 && batch_stride % 4 == 0, "broadcast_rows alignment");
+    const int n4 = rows * d / 4;
+    const int64_t total = static_cast<int64_t>(B) * n4;
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 8));
+    broadcast_rows_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(src), n4, reinterpret_cast<float4*>(dst),
+                                               batch_stride / 4, B);
+    KERNEL_CHECK();
+    count_launch();
+}
+void sum_over_batch_f32(const float* src, int64_t batch_stride, int B, int n, float* out, cudaStream_t s) {
+    sum_over_batch_kernel<<<ceil_div(n, 256), 256, 0, s>>>(src, batch_stride, B, n, out);
+    KERNEL_CHECK();
+    count_launch();
+}
+void fill_zero(void* p, size_t bytes, cudaStream_t s) { CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, s)); }
+
+void layernorm_fwd(const float* x, int ld_x, const int* row_index, const float* gamma, const float* beta, bf16* y,
+                   int ld_y, float* mean, float* rstd, int M, int d, float eps, cudaStream_t s) {
+    EAVQA_CHECK(d % 4 == 0 && d <= 2048 && ld_x % 4 == 0 && ld_y % 4 == 0, "layernorm width must be a multiple of 4 and <= 2048");
+    const int need = ceil_div(d / 4, 32);
+    const int grid = ceil_div(M, 8);
+    if (need <= 4)
+        layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, ld_x, row_index, gamma, beta, y, ld_y, mean, rstd, M, d, eps);
+    else if (need <= 8)
+        layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, ld_x, row_index, gamma, beta, y, ld_y, mean, rstd, M, d, eps);
+    else
+        layernorm_fwd_kernel<16><<<grid, 256, 0, s>>>(x, ld_x, row_index, gamma, beta, y, ld_y, mean, rstd, M, d, eps);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+template <int MAXV>
+static void launch_ln_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, const int* row_index, const float* gamma,
+                          const float* mean, const float* rstd, float* dx, int ld_dx, int accumulate, bf16* dx_bf16,
+                          int ld_dxb, float* dgamma, float* dbeta, int M, int d, cudaStream_t s) {
+    if (dgamma != nullptr) {
+        const int grid = std::min(ceil_div(M, 8), 2 * num_sms());
+        layernorm_bwd_kernel<MAXV, true><<<grid, 256, 2 * d * sizeof(float), s>>>(
+            dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx, accumulate, dx_bf16, ld_dxb, dgamma, dbeta, M, d);
+    } else {
+        const int grid = ceil_div(M, 8);
+        layernorm_bwd_kernel<MAXV, false><<<grid, 256, 0, s>>>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx,
+                                                               ld_dx, accumulate, dx_bf16, ld_dxb, nullptr, nullptr, M, d);
+    }
+    KERNEL_CHECK();
+    count_launch();
+}
+void layernorm_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, const int* row_index, const float* gamma,
+                   const float* mean, const float* rstd, float* dx, int ld_dx, int accumulate, bf16* dx_bf16,
+                   int ld_dxb, float* dgamma, float* dbeta, int M, int d, float eps, cudaStream_t s) {
+    (void)eps;
+    EAVQA_CHECK(d % 4 == 0 && d <= 2048, "layernorm width must be a multiple of 4 and <= 2048");
+    EAVQA_CHECK(mean != nullptr && rstd != nullptr, "layernorm_bwd needs the saved statistics");
+    EAVQA_CHECK((dgamma == nullptr) == (dbeta == nullptr), "dgamma and dbeta go together");
+    const int need = ceil_div(d / 4, 32);
+    if (need <= 4)
+        launch_ln_bwd<4>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx, accumulate, dx_bf16, ld_dxb, dgamma, dbeta, M, d, s);
+    else if (need <= 8)
+        launch_ln_bwd<8>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx, accumulate, dx_bf16, ld_dxb, dgamma, dbeta, M, d, s);
+    else
+        launch_ln_bwd<16>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx, accumulate, dx_bf16, ld_dxb, dgamma, dbeta, M, d, s);
+}
+
+void prepend_plan(const int64_t* tokens, const int64_t* mask, int B, int Tt, int P, int* plan, int* valid, cudaStream_t s) {
+    const int n = B * (P + Tt);
+    prepend_plan_kernel<<<ceil_div(n, 256), 256, 0, s>>>(tokens, mask, B, Tt, P, plan, valid);
+    KERNEL_CHECK();
+    count_launch();
+}
+void splice_plan(const int64_t* tokens, const int64_t* mask, int B, int Tt, int P, int n_img, int64_t sent_lo,
+                 int64_t sent_hi, int* plan, int* valid, int* err_flag, cudaStream_t s) {
+    const int T_out = Tt + (P - 1) * n_img;
+    fill_zero(plan, sizeof(int) * static_cast<size_t>(B) * T_out, s);
+    fill_zero(valid, sizeof(int) * static_cast<size_t>(B) * T_out, s);
+    splice_plan_kernel<<<ceil_div(B * 32, 128), 128, 0, s>>>(tokens, mask, B, Tt, P, n_img, sent_lo, sent_hi, plan, valid, err_flag);
+    KERNEL_CHECK();
+    count_launch();
+}
+void embed_rows(const int* plan, int B, int T, int d, const float* wte, int vocab, const float* prefix,
+                int64_t prefix_batch_stride, int prefix_row_stride, const float* wpe, float* out, cudaStream_t s) {
+    EAVQA_CHECK(d % 4 == 0 && prefix_batch_stride % 4 == 0 && prefix_row_stride % 4 == 0, "embed alignment");
+    const int rows = B * T;
+    embed_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(plan, rows, T, d, wte, vocab, prefix, prefix_batch_stride,
+                                                        prefix_row_stride, wpe, out);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void ce_plan(const int64_t* labels, int B, int Tt, int T, int P, int vocab, int* row_index, int* label, int* n_valid,
+             cudaStream_t s) {
+    fill_zero(n_valid, sizeof(int), s);
+    ce_plan_kernel<<<ceil_div(B * Tt, 256), 256, 0, s>>>(labels, B, Tt, T, P, vocab, row_index, label, n_valid);
+    KERNEL_CHECK();
+    count_launch();
+}
+void ce_finalize(const float2* partial, int tiles, const float* target, const int* label, float* lse, float* loss_sum,
+                 int M, cudaStream_t s) {
+    fill_zero(loss_sum, sizeof(float), s);
+    ce_finalize_kernel<<<ceil_div(M, 8), 256, 0, s>>>(partial, tiles, target, label, lse, loss_sum, M);
+    KERNEL_CHECK();
+    count_launch();
+}
+void ce_loss(const float* loss_sum, const int* n_valid, float* loss_out, cudaStream_t s) {
+    ce_loss_kernel<<<1, 1, 0, s>>>(loss_sum, n_valid, loss_out);
+    KERNEL_CHECK();
+    count_launch();
+}
+void ce_dlogits(bf16* z, int ld, int M, int vocab, int n_cols, const float* lse, const int* label, const int* n_valid,
+                cudaStream_t s) {
+    EAVQA_CHECK(ld % 8 == 0 && n_cols % 8 == 0 && n_cols <= ld, "ce_dlogits alignment");
+    ce_dlogits_kernel<<<M, 256, 0, s>>>(z, ld, vocab, n_cols, lse, label, n_valid);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void greedy_step(const float* logits, int ld, int B, int vocab, int step, int max_new, int has_eos, int64_t pad_id,
+                 int64_t eos_id, int* unfinished, int64_t* tokens_out, int* n_unfinished, float* top_logit,
+                 const float* wte, const float* wpe_row, int d, float* x_next, int* valid_next, int valid_stride,
+                 cudaStream_t s) {
+    greedy_step_kernel<<<B, 256, 0, s>>>(logits, ld, vocab, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out,
+                                         n_unfinished, top_logit, wte, wpe_row, d, x_next, valid_next, valid_stride);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+}  // namespace eavqa

@@ -1,0 +1,82 @@
+// Host launchers of the fused memory-bound kernels and the attention kernels.
+// All launch on the given stream and never synchronise.
+#pragma once
+#include "common.cuh"
+
+namespace eavqa {
+
+void count_launch(int n = 1);
+int64_t kernel_launch_count();
+
+// ---------------------------------------------------------------- packing / layout (elementwise.cu)
+// fp32 [R, C] (ld_src) -> bf16 copy [R, C] (ld_dst) and/or bf16 transpose [C, R] (ld_t) and/or fp32 column sums
+// (atomicAdd into colsum[C]; caller zeroes).  Either destination may be null.
+void convert_transpose_f32(const float* src, int ld_src, int R, int C, bf16* dst, int ld_dst, bf16* dst_t, int ld_t,
+                           float* colsum, cudaStream_t s);
+void convert_transpose_bf16(const bf16* src, int ld_src, int R, int C, bf16* dst_t, int ld_t, float* colsum,
+                            cudaStream_t s);
+// dst[r, :] = src[:]  for r < R   (prefix_const rows of the mapper input), fp32
+void broadcast_rows_f32(const float* src, int rows, int d, float* dst, int64_t batch_stride, int B, cudaStream_t s);
+// out[c] (+)= sum_b src[b*batch_stride + c]   (prefix_const gradient), c < n
+void sum_over_batch_f32(const float* src, int64_t batch_stride, int B, int n, float* out, cudaStream_t s);
+void fill_zero(void* p, size_t bytes, cudaStream_t s);
+
+// ---------------------------------------------------------------- LayerNorm (elementwise.cu)
+// y = LN(x[row]) * gamma + beta, bf16 out; x row = row_index ? row_index[m] : m.  Saves mean / rstd (optional).
+void layernorm_fwd(const float* x, int ld_x, const int* row_index, const float* gamma, const float* beta, bf16* y,
+                   int ld_y, float* mean, float* rstd, int M, int d, float eps, cudaStream_t s);
+// dx[row] = (accumulate ? dx[row] : 0) + LN'(dy) ; optional bf16 copy of the result; optional dgamma/dbeta (atomicAdd).
+// mean / rstd are recomputed from x when null.
+void layernorm_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, const int* row_index, const float* gamma,
+                   const float* mean, const float* rstd, float* dx, int ld_dx, int accumulate, bf16* dx_bf16,
+                   int ld_dxb, float* dgamma, float* dbeta, int M, int d, float eps, cudaStream_t s);
+
+// ---------------------------------------------------------------- embedding / splice (elementwise.cu)
+// plan[b, t] >= 0 : token id ; < 0 : -(prefix_row + 1) ; valid[b, t] = key-validity (attention mask)
+void prepend_plan(const int64_t* tokens, const int64_t* mask, int B, int Tt, int P, int* plan, int* valid, cudaStream_t s);
+// vct0.py:494-533 semantics; sentinel ids in [sent_lo, sent_hi]; err_flag set to 1 when a row does not hold n_img sentinels
+void splice_plan(const int64_t* tokens, const int64_t* mask, int B, int Tt, int P, int n_img, int64_t sent_lo,
+                 int64_t sent_hi, int* plan, int* valid, int* err_flag, cudaStream_t s);
+// h0[b, t, :] = (plan >= 0 ? wte[plan] : prefix[b, -plan-1, :]) + (wpe ? wpe[t] : 0)
+void embed_rows(const int* plan, int B, int T, int d, const float* wte, int vocab, const float* prefix,
+                int64_t prefix_batch_stride, int prefix_row_stride, const float* wpe, float* out, cudaStream_t s);
+
+// ---------------------------------------------------------------- LM head cross-entropy (elementwise.cu)
+// rows r = b*Tt + j predict text token j from hidden row b*T + P-1+j (labels are shifted inside HF, loss_utils.py:57-60)
+void ce_plan(const int64_t* labels, int B, int Tt, int T, int P, int vocab, int* row_index, int* label, int* n_valid,
+             cudaStream_t s);
+// merges per-tile (max, sumexp) partials -> lse[r]; accumulates sum of (lse - target) over valid rows into loss_sum
+void ce_finalize(const float2* partial, int tiles, const float* target, const int* label, float* lse, float* loss_sum,
+                 int M, cudaStream_t s);
+// loss = loss_sum / n_valid (NaN when no valid target, as the reference's mean over an empty set)
+void ce_loss(const float* loss_sum, const int* n_valid, float* loss_out, cudaStream_t s);
+// in place: z[r, v] <- (softmax(z[r])[v] - [v == label[r]]) / n_valid for valid rows, 0 otherwise / for v >= vocab
+void ce_dlogits(bf16* z, int ld, int M, int vocab, int n_cols, const float* lse, const int* label, const int* n_valid,
+                cudaStream_t s);
+
+// ---------------------------------------------------------------- greedy decode bookkeeping (elementwise.cu)
+// per row: nxt = argmax(logits[:vocab]); out = unfinished ? nxt : pad; unfinished &= out != eos;
+// tokens_out[b, step] = out; x_next[b] = wte[nxt] + wpe[pos]; n_unfinished[step] = sum(unfinished)
+void greedy_step(const float* logits, int ld, int B, int vocab, int step, int max_new, int has_eos, int64_t pad_id,
+                 int64_t eos_id, int* unfinished, int64_t* tokens_out, int* n_unfinished, float* top_logit,
+                 const float* wte, const float* wpe_row, int d, float* x_next, int* valid_next, int valid_stride,
+                 cudaStream_t s);
+
+// ---------------------------------------------------------------- attention (attention.cu)
+// GPT-2 causal attention with key-padding mask, head_dim 64, qkv [B*T, 3d] bf16 (q | k | v, heads contiguous).
+// o [B*T, d] bf16; lse [B, H, T] fp32 (of scaled scores).
+void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, int B, int T, int H, cudaStream_t s);
+// dqkv [B*T, 3d] bf16; dq_scratch fp32 [B*T, d] (only touched when T > 64)
+void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf16* d_o, const float* lse, bf16* dqkv,
+                      float* dq_scratch, int B, int T, int H, cudaStream_t s);
+// KV cache: [B, Tmax, 2d] bf16 per layer (k | v per token)
+void kv_cache_fill(const bf16* qkv, bf16* cache, int B, int T, int Tmax, int d, cudaStream_t s);
+// one new query per (b, h): appends this step's k, v at position pos and attends over keys [0, pos] where valid
+void lm_attention_decode(const bf16* qkv_new, bf16* cache, const int* valid, int valid_stride, bf16* o, int B, int H,
+                         int pos, int Tmax, cudaStream_t s);
+
+// mapper self-attention (no mask), S = clip_length + prefix_length small, any head_dim: qkv [B*S, 3d] bf16
+void mapper_attention_fwd(const bf16* qkv, bf16* o, int B, int S, int H, int hd, cudaStream_t s);
+void mapper_attention_bwd(const bf16* qkv, const bf16* d_o, bf16* dqkv, int B, int S, int H, int hd, cudaStream_t s);
+
+}  // namespace eavqa

@@ -1,0 +1,136 @@
+/*
+ * eavqa_b200 -- C ABI of the B200-native CLIP-prefix language-model step.
+ *
+ * Drop-in boundary for ONE path of rs-anderson/explicit-alignment-for-vqa-tasks: the model object that
+ * `ClipCapExecutor` builds and calls (reference `src/trainers/clipcap_exector.py:52-56,165-171,236-243`),
+ * i.e. `ClipCaptionPrefix` of `src/models/clipcap.py:240-471,590-599` plus the in-context prefix splice of
+ * `src/models/vct0.py:494-533`.  The reference is pure Python and has no FFI; each entry point below names
+ * the reference interface it replaces.  The Python host (`eavqa_b200.model.ClipCaptionPrefixB200`) binds
+ * these with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; `eavqa_last_error()` then returns a
+ *     thread-local, NUL-terminated message.  Nothing throws across this boundary.
+ *   - all tensor arguments are raw DEVICE pointers owned by the caller (torch); the library borrows them for
+ *     the duration of the call and never retains them, except weights passed to `eavqa_load_lm_weight`,
+ *     which are copied/packed.  Workspace, packed weights and the KV cache are owned by the handle.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; the caller's current torch stream)
+ *     and is asynchronous; only `eavqa_generate` synchronises that stream once, at its end, to return the
+ *     number of steps taken.  One handle per process/GPU; calls on one handle are not re-entrant.
+ *   - there is no CPU path: every entry point fails if no sm_100 device is current.
+ */
+#ifndef EAVQA_B200_H
+#define EAVQA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden: only this ABI is exported */
+#endif
+
+#define EAVQA_ABI_VERSION 1
+
+typedef struct eavqa_handle eavqa_handle;
+
+enum { EAVQA_MAPPER_MLP = 0, EAVQA_MAPPER_TRANSFORMER = 1 };
+enum { EAVQA_F32 = 0, EAVQA_BF16 = 1 };
+
+/* Mirrors `ClipCaptionModel.__init__` kwargs (clipcap.py:240-249: prefix_length, clip_length, prefix_size,
+ * num_layers, mapping_type) and the GPT2Config fields of the LM named by `model_version` (clipcap.py:252). */
+typedef struct eavqa_config {
+    int32_t n_layer, n_head, d_model;   /* GPT-2: 12/12/768, 24/16/1024, 36/20/1280, 48/25/1600; head_dim must be 64 */
+    int32_t vocab, n_positions;         /* 50257 (+ added special tokens, clipcap_exector.py:56), 1024 */
+    int32_t prefix_length, clip_length; /* P, and the transformer mapper's clip_length (clipcap.py:213-237) */
+    int32_t clip_dim;                   /* prefix_size: 512 (ViT-B/32) or 768 (ViT-L/14) */
+    int32_t mapper_type;                /* EAVQA_MAPPER_* ("mlp" vs anything else, clipcap.py:254-271) */
+    int32_t mapper_layers;              /* num_layers of the transformer mapper (8) */
+} eavqa_config;
+
+const char* eavqa_last_error(void);
+int eavqa_abi_version(void);
+
+/* ClipCaptionModel.__init__ (clipcap.py:240-272) */
+int eavqa_create(const eavqa_config* cfg, eavqa_handle** out);
+int eavqa_destroy(eavqa_handle* h);
+
+/* GPT2LMHeadModel.from_pretrained (clipcap.py:252) + resize_token_embeddings (clipcap_exector.py:56):
+ * one call per HF state-dict tensor ("transformer.wte.weight", "transformer.h.0.attn.c_attn.weight", ...),
+ * fp32 or bf16, `numel` elements on the device; the tensor is copied and packed.  `eavqa_finalize_lm`
+ * checks that every tensor arrived. */
+int eavqa_load_lm_weight(eavqa_handle* h, const char* name, const void* dev_ptr, int32_t dtype, int64_t numel, void* stream);
+int eavqa_finalize_lm(eavqa_handle* h, void* stream);
+
+/* Layout of the flat fp32 mapper parameter / gradient buffers: entries in the reference's
+ * `clip_project.named_parameters()` order (clipcap.py:256-271). */
+int64_t eavqa_mapper_param_count(const eavqa_handle* h);   /* total elements */
+int32_t eavqa_mapper_num_tensors(const eavqa_handle* h);
+int eavqa_mapper_tensor_info(const eavqa_handle* h, int32_t index, char* name_out, size_t name_cap, int64_t* offset,
+                             int64_t* rows, int64_t* cols);
+
+/* ClipCaptionModel.forward (clipcap.py:290-342) + loss.backward() restricted to clip_project
+ * (ClipCaptionPrefix, clipcap.py:590-599).
+ *   clip   [B, clip_dim] fp32        tokens / mask / labels [B, text_len] int64 (labels: -100 = ignore)
+ *   params [param_count] fp32        grads [param_count] fp32 (overwritten; NULL = forward only)
+ *   loss_out: device fp32 scalar */
+int eavqa_train_step(eavqa_handle* h, int32_t batch, int32_t text_len, const float* clip, const int64_t* tokens,
+                     const int64_t* mask, const int64_t* labels, const float* params, float* grads, float* loss_out,
+                     void* stream);
+
+/* ClipCaptionModel.generate + _generate_from_embeddings (clipcap.py:344-471), with the k-shot prompt assembly of
+ * VCT0Model.generate / insert_prefix_into_input (vct0.py:446-464,494-533) when n_images > 0.
+ *   n_images = 0 : one prefix is prepended (clip [B, clip_dim]);
+ *   n_images >= 1: clip [B, n_images, clip_dim]; each token id in [sentinel_lo, sentinel_hi] is replaced by the
+ *                  next image's P prefix rows; every row must hold exactly n_images sentinels.
+ *   tokens_out [B, max_new] int64 (device); has_eos = 0 reproduces eos_token_id=None.
+ *   top_logit  [B, max_new] fp32 (device) or NULL: the winning logit of every step (diagnostics).
+ *   steps_out  (host int32): number of decode steps executed before every row had finished (clipcap.py:463);
+ *              only tokens_out[:, :steps_out] is meaningful. */
+int eavqa_generate(eavqa_handle* h, int32_t batch, int32_t text_len, int32_t n_images, const float* clip,
+                   const int64_t* tokens, const int64_t* mask, int64_t sentinel_lo, int64_t sentinel_hi,
+                   const float* params, int32_t max_new, int32_t has_eos, int64_t pad_id, int64_t eos_id,
+                   int64_t* tokens_out, float* top_logit, int32_t* steps_out, void* stream);
+
+/* VCT0Model.insert_prefix_into_input (vct0.py:494-533) on caller-supplied embeddings (golden-vector parity).
+ *   text_table [vocab, d] fp32 rows looked up by token id; prefix [B, n_images*P, d] fp32
+ *   out_emb [B, T_out, d] fp32, out_mask [B, T_out] int32, T_out = text_len + (P-1)*n_images */
+int eavqa_splice(int32_t batch, int32_t text_len, int32_t n_images, int32_t prefix_length, int32_t d, int32_t vocab,
+                 const int64_t* tokens, const int64_t* mask, int64_t sentinel_lo, int64_t sentinel_hi,
+                 const float* text_table, const float* prefix, float* out_emb, int32_t* out_mask, void* stream);
+
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t eavqa_launch_count(void);
+
+/* ---- single-operator entry points (unit parity tests of each kernel; same kernels the step uses) ---- */
+/* D[M,N] = epi(A[M,K] * B[N,K]^T): bf16 operands, fp32 accumulate (tcgen05/TMEM); act/dact: see csrc/gemm.cuh */
+int eavqa_op_gemm(const void* A, int32_t lda, const void* B, int32_t ldb, int32_t M, int32_t N, int32_t K, void* out,
+                  int32_t ldo, int32_t out_fp32, const float* bias, const float* residual, int32_t ld_res, int32_t act,
+                  const void* aux, int32_t ld_aux, int32_t dact, void* out2, int32_t ldo2, int32_t block_n, void* stream);
+/* LM-head GEMM with fused softmax statistics: logits bf16 [M, ldo], lse [M] and target logit [M] */
+int eavqa_op_lmhead_ce(const void* H, const void* W, int32_t M, int32_t vocab, int32_t n_cols, int32_t K, const int32_t* label,
+                       void* logits, int32_t ldo, float* lse, float* target, float* loss_sum, void* stream);
+int eavqa_op_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                           int32_t M, int32_t d, void* stream);
+int eavqa_op_layernorm_bwd(const void* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                           float* dx, int32_t accumulate, void* dx_bf16, float* dgamma, float* dbeta, int32_t M, int32_t d,
+                           void* stream);
+int eavqa_op_lm_attention_fwd(const void* qkv, const int32_t* valid, void* o, float* lse, int32_t B, int32_t T, int32_t H,
+                              void* stream);
+int eavqa_op_lm_attention_bwd(const void* qkv, const int32_t* valid, const void* o, const void* d_o, const float* lse,
+                              void* dqkv, float* dq_scratch, int32_t B, int32_t T, int32_t H, void* stream);
+int eavqa_op_mapper_attention_fwd(const void* qkv, void* o, int32_t B, int32_t S, int32_t H, int32_t hd, void* stream);
+int eavqa_op_mapper_attention_bwd(const void* qkv, const void* d_o, void* dqkv, int32_t B, int32_t S, int32_t H, int32_t hd,
+                                  void* stream);
+int eavqa_op_convert_transpose(const float* src, int32_t R, int32_t C, void* dst, void* dst_t, int32_t ld_t, float* colsum,
+                               void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAVQA_B200_H */
