@@ -67,8 +67,9 @@ def test_gemm_plain_fp32_out(L, shape, block_n):
     """tcgen05 GEMM, fp32 output: bf16 products accumulate in fp32, so only summation order differs from torch:
     |err| <= 2e-3 * sqrt(K) * scale."""
     M, N, K = shape
-    A = _rand((M, K), 1, dtype=torch.bfloat16)
-    B = _rand((N, K), 2, dtype=torch.bfloat16)
+    Kp = (K + 7) // 8 * 8          # row strides must be multiples of 8 elements; K itself may be ragged
+    A = _rand((M, Kp), 1, dtype=torch.bfloat16)[:, :K]
+    B = _rand((N, Kp), 2, dtype=torch.bfloat16)[:, :K]
     out, _ = gemm(L, A, B, out_fp32=True, block_n=block_n)
     ref = A.float() @ B.float().t()
     err = (out - ref).abs().max().item()
