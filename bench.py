@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- CLIP-prefix LM step on B200 (BASELINE.json metric: mapper train samples/s; few-shot answers/s).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                      # this repo's CUDA path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W                       # data-parallel, weak scaling (256 samples / GPU)
+    python bench.py --impl reference --steps K --warmup W               # the CPU port of the reference path (oracle)
+
+One JSON line on stdout (rank 0).  A "step" = forward + backward-to-the-mapper + caption cross-entropy of one
+synthetic Conceptual-Captions batch (BASELINE.json configs[1]: GPT-2 small, transformer mapper, batch 256 per
+GPU, bf16 tensor-core math with fp32 accumulate), the NCCL all-reduce of the mapper gradients when N > 1, and the
+fused AdamW update of the mapper.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# ---- workload ------------------------------------------------------------------------------------
+C2 = dict(model_version="gpt2", mapping_type="transformer", prefix_length=10, clip_length=10, clip_dim=512, num_layers=8,
+          batch_per_gpu=256, text_len=40, vocab=50257)
+C4 = dict(model_version="gpt2-medium", mapping_type="mlp", prefix_length=10, clip_length=10, clip_dim=512, num_layers=8,
+          batch=128, num_shots=4, max_length=10)
+GFLOP_PER_SAMPLE_C2 = 27.88          # algorithmic work per sample: LM 23.30 + transformer mapper 4.58
+CPU_SAMPLE_BATCH = 8                 # bounded CPU sample: the same config at batch 8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops=float(d["bf16_tflops_sustained"]), tflops_burst=float(d["bf16_tflops"]), hbm=float(d["hbm_gbs"]),
+                    source="MEASURED_PEAKS.json (sustained bf16 GEMM, kernel timed inside a long step)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback of B200_PROFILING.md (file absent)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---- the CPU port of the reference path (oracle), used for --impl reference and cpu_baseline --------------------
+def cpu_reference(steps: int, warmup: int):
+    from oracle import clip_prefix_lm as orc
+    import eavqa_b200.synthetic as syn
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg_lm = syn.lm_config(C2["model_version"], vocab=C2["vocab"])
+    lm_w = syn.make_lm_weights(cfg_lm, seed=0)
+    mapper_w = syn.make_mapper_params(C2["mapping_type"], C2["clip_dim"], cfg_lm["d_model"], C2["prefix_length"], C2["clip_length"],
+                                      C2["num_layers"], seed=1)
+    batch = syn.make_caption_batch(CPU_SAMPLE_BATCH, C2["text_len"], C2["clip_dim"], C2["vocab"], seed=2021)
+    cfg = dict(n_layer=cfg_lm["n_layer"], n_head=cfg_lm["n_head"], d_model=cfg_lm["d_model"], prefix_length=C2["prefix_length"],
+               clip_length=C2["clip_length"], mapping_type=C2["mapping_type"], num_layers=C2["num_layers"])
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.train_step(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"], batch["attention_mask"], batch["labels"])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return dict(value=CPU_SAMPLE_BATCH / sec, unit="samples/s", cores=torch.get_num_threads(), kind="port",
+                sample="same config at batch %d (fp32, %d timed steps of forward+backward, oracle/clip_prefix_lm.py)" % (CPU_SAMPLE_BATCH, steps),
+                ms_per_step=sec * 1e3)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 40)), max(1, min(args.warmup, 5))
+    r = cpu_reference(steps, warmup)
+    line = {"impl": "reference", "metric": "mapper_train_samples_per_sec", "value": r["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(1, note="CPU port of the reference path on the host cores; bounded sample"),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world, note=""):
+    return {"workload": "Conceptual Captions mapper training step, BASELINE configs[1]: frozen GPT-2 small (d=768, L=12, V=50257), "
+                        "transformer mapper (8 layers, 8 heads, clip_length 10), prefix 10, text 40 (T=50), synthetic CLIP ViT-B/32 "
+                        "512-d embeddings", "batch_per_gpu": C2["batch_per_gpu"], "global_batch": C2["batch_per_gpu"] * world,
+            "parallelism": "dp%d" % world, "optimizer": "fused AdamW on the mapper (in the timed region)",
+            "l2": "inputs larger than L2: ~3 GB of activations per step >> 126 MB L2, no flush needed", "note": note}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-generate", action="store_true", help="skip the few-shot answers/s leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-report", default="", help="write the per-shape GEMM timing report to this file")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU path (use --impl reference for the CPU port)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import eavqa_b200
+    import eavqa_b200.synthetic as syn
+    from eavqa_b200 import lib
+    from eavqa_b200.optim import FlatAdamW
+    L = lib.load()
+
+    lm_cfg = syn.lm_config(C2["model_version"], vocab=C2["vocab"])
+    lm_w = syn.make_lm_weights(lm_cfg, seed=0)
+    torch.manual_seed(1)
+    model = eavqa_b200.ClipCaptionPrefixB200(prefix_length=C2["prefix_length"], clip_length=C2["clip_length"],
+                                             prefix_size=C2["clip_dim"], num_layers=C2["num_layers"],
+                                             mapping_type=C2["mapping_type"], model_version=C2["model_version"],
+                                             lm_state_dict=lm_w).to(dev).train()
+    B = C2["batch_per_gpu"]
+    host = syn.make_caption_batch(B, C2["text_len"], C2["clip_dim"], C2["vocab"], seed=2021 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    opt = FlatAdamW(model, lr=1e-4)
+
+    def step(b):
+        out = model(question_tokens=b["input_ids"], labels=b["labels"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"])
+        out.loss.backward()
+        g = model.last_flat_grads
+        if world > 1:
+            dist.all_reduce(g)                               # sum; the 1/W of the DDP mean is folded into AdamW
+        opt.step(g, grad_scale=1.0 / world)
+        opt.zero_grad()
+        return out.loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms) / n
+
+    # ---- kernel-resident throughput: inputs already in HBM ---------------------------------------------------------
+    for _ in range(args.warmup):
+        step(resident)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.eavqa_launch_count()
+    ms_step = timed(lambda: step(resident), args.steps)
+    launches = (L.eavqa_launch_count() - launches0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- end to end through the public API: pinned host batch -> H2D -> step -> loss read back ------------------------
+    def e2e_step():
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        loss = step(b)
+        return float(loss)                                   # D2H of the step's result
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    e2e = {"value": B * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "ms_per_step": ms_e2e}
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events, outside the timed region --------------
+    import ctypes as C
+    pk = peaks()
+    prof_steps = 3
+    lib.check(L.eavqa_profile_begin())
+    for _ in range(prof_steps):
+        step(resident)
+    tot_ms, tot_fl, nl = C.c_double(), C.c_double(), C.c_int64()
+    rep = C.create_string_buffer(1 << 16)
+    lib.check(L.eavqa_profile_end(C.byref(tot_ms), C.byref(tot_fl), C.byref(nl), rep, len(rep)))
+    gemm_ms, gemm_tf = tot_ms.value / prof_steps, tot_fl.value / prof_steps / 1e12
+    achieved = gemm_tf / (gemm_ms * 1e-3)
+    step_tflops = GFLOP_PER_SAMPLE_C2 * B / 1e3 / (ms_step * 1e-3)
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM, all GEMMs of the step)", "achieved": achieved,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                "peak_source": pk["source"], "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": gemm_tf,
+                "gemm_launches_per_step": nl.value // prof_steps, "gemm_share_of_step": gemm_ms / ms_step,
+                "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / pk["tflops"],
+                "algorithmic_gflop_per_sample": GFLOP_PER_SAMPLE_C2}
+    if args.profile_report and rank == 0:
+        with open(args.profile_report, "w") as f:
+            f.write(rep.value.decode())
+
+    line = {"metric": "mapper_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline}
+
+    # ---- few-shot VQA answers/s (BASELINE configs[3]) and the CPU baseline: rank 0, N = 1 only ------------------------
+    del model, opt
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_generate:
+        line["few_shot_generate"] = bench_generate(dev, eavqa_b200, syn, args)
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(steps=6, warmup=2)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_generate(dev, eavqa_b200, syn, args):
+    c = C4
+    k = c["num_shots"]
+    lm_cfg = syn.lm_config(c["model_version"], vocab=50257 + k + 1)
+    lm_w = syn.make_lm_weights(lm_cfg, seed=0, hot_rows=512)
+    torch.manual_seed(1)
+    model = eavqa_b200.ClipCaptionPrefixB200(prefix_length=c["prefix_length"], clip_length=c["clip_length"], prefix_size=c["clip_dim"],
+                                             num_layers=c["num_layers"], mapping_type=c["mapping_type"],
+                                             model_version=c["model_version"], lm_state_dict=lm_w,
+                                             special_token_id=50257 + k).to(dev).eval()
+    host = syn.make_fewshot_batch(c["batch"], k, c["clip_dim"], lm_cfg["vocab"], 50257 + k, seed=2021, pad_token_id=50256)
+    host = {kk: v.pin_memory() for kk, v in host.items()}
+
+    def gen():
+        b = {kk: v.to(dev, non_blocking=True) for kk, v in host.items()}
+        # eos_token_id=None: every row decodes all max_length tokens (worst case; no early exit)
+        return model.generate(question_tokens=b["input_ids"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"],
+                              max_length=c["max_length"], pad_token_id=50256, eos_token_id=None)
+    model.gpt.config.eos_token_id = None
+    for _ in range(3):
+        gen()
+    n = max(3, min(args.steps, 10))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        out = gen()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    T0 = host["input_ids"].shape[1] + 9 * (k + 1)
+    return {"metric": "few_shot_vqa_answers_per_sec", "value": c["batch"] / (ms * 1e-3), "unit": "answers/s", "ms_per_batch": ms,
+            "config": {"workload": "BASELINE configs[3]: 4-shot in-context prefixes, GPT-2 medium, batch 128, 10 new tokens, "
+                                   "KV-cached greedy decode, host tensors in / token tensor out", "prompt_len": T0,
+                       "tokens_out_shape": list(out.shape)},
+            "algorithmic_gflop_per_answer": 82.8, "tflops": 82.8 * c["batch"] / 1e3 / (ms * 1e-3)}
+
+
+if __name__ == "__main__":
+    main()

@@ -235,4 +235,29 @@ int eavqa_op_convert_transpose(const float* src, int32_t R, int32_t C, void* dst
     API_END
 }
 
+int eavqa_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
+    API_BEGIN
+    EAVQA_CHECK(params && grads && exp_avg && exp_avg_sq, "null argument");
+    adamw_step(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
+    API_END
+}
+
+int eavqa_profile_begin(void) {
+    API_BEGIN
+    gemm_profile_begin();
+    API_END
+}
+
+int eavqa_profile_end(double* total_ms, double* total_flops, int64_t* launches, char* report, size_t report_cap) {
+    API_BEGIN
+    std::string rep;
+    gemm_profile_end(total_ms, total_flops, launches, &rep);
+    if (report != nullptr && report_cap > 0) {
+        std::strncpy(report, rep.c_str(), report_cap - 1);
+        report[report_cap - 1] = 0;
+    }
+    API_END
+}
+
 }  // extern "C"

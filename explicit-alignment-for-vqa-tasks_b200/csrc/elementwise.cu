@@ -484,9 +484,45 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
     }
 }
 
+__global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                    float4* __restrict__ v, int64_t n4, float lr, float beta1, float beta2,
+                                                    float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+        float* pa = reinterpret_cast<float*>(&pp);
+        float* ga = reinterpret_cast<float*>(&gg);
+        float* ma = reinterpret_cast<float*>(&mm);
+        float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = ga[k] * gscale;
+            pa[k] *= 1.0f - lr * wd;
+            ma[k] = beta1 * ma[k] + (1.0f - beta1) * gr;
+            va[k] = beta2 * va[k] + (1.0f - beta2) * gr * gr;
+            const float denom = sqrtf(va[k]) / bc2_sqrt + eps;
+            pa[k] -= (lr / bc1) * (ma[k] / denom);
+        }
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+
 }  // namespace
 
 // ============================================================================================ launchers
+void adamw_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, int step, float grad_scale, cudaStream_t s) {
+    EAVQA_CHECK(n % 4 == 0 && step >= 1, "adamw_step: n must be a multiple of 4 and step >= 1");
+    const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+    const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(n / 4, 256), static_cast<int64_t>(num_sms()) * 8));
+    adamw_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads),
+                                      reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n / 4, lr, beta1, beta2, eps,
+                                      weight_decay, bc1, sqrtf(bc2), grad_scale);
+    KERNEL_CHECK();
+    count_launch();
+}
+
 void convert_transpose_f32(const float* src, int ld_src, int R, int C, bf16* dst, int ld_dst, bf16* dst_t, int ld_t,
                            float* colsum, cudaStream_t s) {
     dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);

@@ -6,6 +6,8 @@
 // weight, the copy whose contraction dimension is contiguous (frozen LM weights are packed once
 // in both orientations; the trainable mapper's are re-packed each step by pack_weight_kernel).
 #pragma once
+#include <string>
+
 #include "common.cuh"
 
 namespace eavqa {
@@ -50,5 +52,9 @@ int gemm_pick_block_n(int M, int N, int K, int forced);
 void gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream);
 // kernels this translation unit launched since process start (bench.py's gpu_launches)
 int64_t gemm_launch_count();
+// per-launch CUDA-event timing of the GEMM kernel (bench.py's roofline leg): begin() arms it, end() synchronises,
+// returns total kernel milliseconds / FLOPs (2MNK) / launches and a per-shape text report
+void gemm_profile_begin();
+void gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches, std::string* report);
 
 }  // namespace eavqa

@@ -11,6 +11,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -19,6 +20,50 @@ namespace eavqa {
 
 static std::atomic<int64_t> g_gemm_launches{0};
 int64_t gemm_launch_count() { return g_gemm_launches.load(); }
+
+struct ProfRec {
+    cudaEvent_t start, stop;
+    int M, N, K, bn;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+void gemm_profile_begin() {
+    g_prof.clear();
+    g_prof_on = true;
+}
+void gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches, std::string* report) {
+    g_prof_on = false;
+    CUDA_CHECK(cudaDeviceSynchronize());
+    std::map<std::tuple<int, int, int, int>, std::pair<double, int>> by_shape;
+    double ms_sum = 0, fl_sum = 0;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, r.start, r.stop));
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+        ms_sum += ms;
+        fl_sum += 2.0 * r.M * r.N * r.K;
+        auto& e = by_shape[std::make_tuple(r.M, r.N, r.K, r.bn)];
+        e.first += ms;
+        e.second += 1;
+    }
+    if (total_ms) *total_ms = ms_sum;
+    if (total_flops) *total_flops = fl_sum;
+    if (launches) *launches = static_cast<int64_t>(g_prof.size());
+    if (report) {
+        report->clear();
+        for (auto& kv : by_shape) {
+            const int M = std::get<0>(kv.first), N = std::get<1>(kv.first), K = std::get<2>(kv.first), bn = std::get<3>(kv.first);
+            const double ms = kv.second.first / kv.second.second;
+            char line[256];
+            snprintf(line, sizeof(line), "M=%d N=%d K=%d bn=%d launches=%d avg_ms=%.4f tflops=%.1f\n", M, N, K, bn,
+                     kv.second.second, ms, 2.0 * M * N * K / (ms * 1e-3) / 1e12);
+            *report += line;
+        }
+    }
+    g_prof.clear();
+}
 
 int num_sms() {
     static int n = 0;
@@ -404,8 +449,19 @@ void launch(const GemmArgs& a, cudaStream_t stream) {
     CUtensorMap mb = make_map(a.B, a.N, a.K, a.ldb, BN);
     const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    ProfRec rec;
+    if (g_prof_on) {
+        CUDA_CHECK(cudaEventCreate(&rec.start));
+        CUDA_CHECK(cudaEventCreate(&rec.stop));
+        rec.M = a.M; rec.N = a.N; rec.K = a.K; rec.bn = BN;
+        CUDA_CHECK(cudaEventRecord(rec.start, stream));
+    }
     gemm_bf16_tn_kernel<BN, CE><<<grid, NUM_THREADS, C::SMEM, stream>>>(ma, mb, a.M, a.N, a.K, a.ep);
     KERNEL_CHECK();
+    if (g_prof_on) {
+        CUDA_CHECK(cudaEventRecord(rec.stop, stream));
+        g_prof.push_back(rec);
+    }
     g_gemm_launches.fetch_add(1);
 }
 

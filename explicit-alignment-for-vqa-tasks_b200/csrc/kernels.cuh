@@ -62,6 +62,12 @@ void greedy_step(const float* logits, int ld, int B, int vocab, int step, int ma
                  const float* wte, const float* wpe_row, int d, float* x_next, int* valid_next, int valid_stride,
                  cudaStream_t s);
 
+// ---------------------------------------------------------------- optimiser (elementwise.cu)
+// torch.optim.AdamW semantics on the flat mapper buffer (clipcap_exector.py:79-81): decoupled weight decay,
+// bias correction; g = grads * grad_scale
+void adamw_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, int step, float grad_scale, cudaStream_t s);
+
 // ---------------------------------------------------------------- attention (attention.cu)
 // GPT-2 causal attention with key-padding mask, head_dim 64, qkv [B*T, 3d] bf16 (q | k | v, heads contiguous).
 // o [B*T, d] bf16; lse [B, H, T] fp32 (of scaled scores).

@@ -104,6 +104,18 @@ int eavqa_splice(int32_t batch, int32_t text_len, int32_t n_images, int32_t pref
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t eavqa_launch_count(void);
 
+/* torch.optim.AdamW (clipcap_exector.py:79-81) on the flat mapper buffer, one fused pass:
+ * params/grads/exp_avg/exp_avg_sq [n] fp32 on the device; `step` counts from 1; g = grads * grad_scale
+ * (grad_scale folds the 1/world_size of the data-parallel mean into the update). */
+int eavqa_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* Per-launch CUDA-event timing of the tcgen05 GEMM kernel (the dominant kernel; bench.py's roofline leg).
+ * begin() arms it; end() synchronises the device and returns summed kernel milliseconds, FLOPs (2MNK) and
+ * launch count since begin(), plus a per-shape text report.  Not for use inside a timed region. */
+int eavqa_profile_begin(void);
+int eavqa_profile_end(double* total_ms, double* total_flops, int64_t* launches, char* report, size_t report_cap);
+
 /* ---- single-operator entry points (unit parity tests of each kernel; same kernels the step uses) ---- */
 /* D[M,N] = epi(A[M,K] * B[N,K]^T): bf16 operands, fp32 accumulate (tcgen05/TMEM); act/dact: see csrc/gemm.cuh */
 int eavqa_op_gemm(const void* A, int32_t lda, const void* B, int32_t ldb, int32_t M, int32_t N, int32_t K, void* out,
