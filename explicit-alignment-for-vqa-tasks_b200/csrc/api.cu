@@ -163,7 +163,7 @@ int eavqa_op_lmhead_ce(const void* H, const void* W, int32_t M, int32_t vocab, i
                        void* logits, int32_t ldo, float* lse, float* target, float* loss_sum, void* stream) {
     API_BEGIN
     const int bn = gemm_pick_block_n(M, n_cols, K, 0);
-    const int tiles = ceil_div(n_cols, bn);
+    const int tiles = 2 * ceil_div(n_cols, bn);
     float2* partial = nullptr;
     CUDA_CHECK(cudaMalloc(&partial, sizeof(float2) * static_cast<size_t>(M) * tiles));
     try {

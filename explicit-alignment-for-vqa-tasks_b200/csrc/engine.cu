@@ -496,7 +496,7 @@ void Engine::train_step(int B, int Tt, const float* clip, const int64_t* tokens,
     EAVQA_CHECK(T <= cfg_.n_positions, "sequence longer than n_positions");
     const bool bwd = grads != nullptr;
     const int head_bn = gemm_pick_block_n(Mh, Vpad_, d, 0);
-    const int head_tiles = ceil_div(Vpad_, head_bn);
+    const int head_tiles = 2 * ceil_div(Vpad_, head_bn);   // one (max, sum-exp) pair per half N-tile
 
     MapperW mw;
     MapperFwd mf;

@@ -31,7 +31,7 @@ struct GemmEpilogue {
     int dact = DACT_NONE;
     // ---- fused softmax-cross-entropy statistics (LM head): per row and per N-tile running
     //      (max, sum exp) over columns < n_valid, plus the fp32 logit of the row's label.
-    float2* ce_partial = nullptr;    // [M, ce_tiles]
+    float2* ce_partial = nullptr;    // [M, ce_tiles], ce_tiles = 2 * ceil(N / block_n) (one pair per half tile)
     float* ce_target = nullptr;      // [M]
     const int* ce_label = nullptr;   // [M], -1 = none
     int ce_tiles = 0;
