@@ -83,7 +83,7 @@ __device__ __forceinline__ void warp_gemm_nt(float (&acc)[8][4], const uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(128) lm_attention_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
+__global__ void __launch_bounds__(128, 4) lm_attention_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
                                                                bf16* __restrict__ o, float* __restrict__ lse, int T,
                                                                int H) {
     __shared__ __align__(16) bf16 Qs[BLK * LDS];
@@ -381,6 +381,170 @@ __global__ void __launch_bounds__(128) lm_attention_bwd_kernel(const bf16* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------ backward, T <= 64
+// The training shapes (T = 50) fit one 64 x 64 block: no loops, no dQ scratch, and the three gradient GEMMs run
+// one after another so that only one 32-register accumulator is live at a time (round-1 ncu: the general kernel
+// needs 252 registers -> 2 CTAs / SM, 12 % warp occupancy, 84 us; this one is capped at 128 -> 4 CTAs / SM).
+__global__ void __launch_bounds__(128, 4) lm_attention_bwd_single_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
+                                                                         const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                                                                         const float* __restrict__ lse, bf16* __restrict__ dqkv,
+                                                                         int T, int H) {
+    extern __shared__ __align__(16) uint8_t smem_bwd[];
+    bf16* Qs = reinterpret_cast<bf16*>(smem_bwd);
+    bf16* Ks = Qs + BLK * LDS;
+    bf16* Vs = Ks + BLK * LDS;
+    bf16* dOs = Vs + BLK * LDS;
+    bf16* Ps = dOs + BLK * LDS;
+    bf16* dSs = Ps + BLK * LDS;
+    float* Ds = reinterpret_cast<float*>(dSs + BLK * LDS);
+    float* Ls = Ds + BLK;
+    int* kvalid = reinterpret_cast<int*>(Ls + BLK);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int d = H * HD;
+    const int64_t ld = 3 * d;
+    const bf16* base = qkv + static_cast<int64_t>(b) * T * ld + h * HD;
+    const bf16* obase = o + static_cast<int64_t>(b) * T * d + h * HD;
+    const bf16* dobase = d_o + static_cast<int64_t>(b) * T * d + h * HD;
+    bf16* dbase = dqkv + static_cast<int64_t>(b) * T * ld + h * HD;
+    const float scale = 0.125f;
+
+    load_tile(Qs, base, ld, 0, T, tid);
+    load_tile(Ks, base + d, ld, 0, T, tid);
+    load_tile(Vs, base + 2 * d, ld, 0, T, tid);
+    load_tile(dOs, dobase, d, 0, T, tid);
+    if (tid < BLK) kvalid[tid] = (tid < T) ? valid[b * T + tid] : 0;
+    {   // D = rowsum(dO * O), lse: two threads per query row
+        const int r = tid >> 1, half = tid & 1;
+        float acc = 0.f;
+        if (r < T) {
+            const uint4* op = reinterpret_cast<const uint4*>(obase + static_cast<int64_t>(r) * d + half * 32);
+            const uint4* dp = reinterpret_cast<const uint4*>(dobase + static_cast<int64_t>(r) * d + half * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 a = op[c], bb = dp[c];
+                float2 x, y;
+                x = unpack_bf16x2(a.x); y = unpack_bf16x2(bb.x); acc += x.x * y.x + x.y * y.y;
+                x = unpack_bf16x2(a.y); y = unpack_bf16x2(bb.y); acc += x.x * y.x + x.y * y.y;
+                x = unpack_bf16x2(a.z); y = unpack_bf16x2(bb.z); acc += x.x * y.x + x.y * y.y;
+                x = unpack_bf16x2(a.w); y = unpack_bf16x2(bb.w); acc += x.x * y.x + x.y * y.y;
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (half == 0) {
+            Ds[r] = acc;
+            Ls[r] = (r < T) ? lse[(static_cast<int64_t>(b) * H + h) * T + r] : 0.f;
+        }
+    }
+    __syncthreads();
+    {
+        uint32_t af[4][4];
+        float sacc[8][4], dpacc[8][4];
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { sacc[x][e] = 0.f; dpacc[x][e] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) load_a(af[ks], Qs, warp * 16, ks * 16, lane);
+        warp_gemm_nt(sacc, af, Ks, lane);                      // S = Q K^T
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) load_a(af[ks], dOs, warp * 16, ks * 16, lane);
+        warp_gemm_nt(dpacc, af, Vs, lane);                     // dP = dO V^T
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float p[4], ds[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = nt * 8 + 2 * t4 + (e & 1);
+                const int row = warp * 16 + g + ((e >> 1) << 3);
+                const bool ok = kvalid[col] && (col <= row) && (row < T);
+                p[e] = ok ? __expf(sacc[nt][e] * scale - Ls[row]) : 0.f;
+                ds[e] = p[e] * (dpacc[nt][e] - Ds[row]);
+            }
+            const int r0 = warp * 16 + g, c0 = nt * 8 + 2 * t4;
+            *reinterpret_cast<uint32_t*>(Ps + r0 * LDS + c0) = pack_bf16x2(p[0], p[1]);
+            *reinterpret_cast<uint32_t*>(Ps + (r0 + 8) * LDS + c0) = pack_bf16x2(p[2], p[3]);
+            *reinterpret_cast<uint32_t*>(dSs + r0 * LDS + c0) = pack_bf16x2(ds[0], ds[1]);
+            *reinterpret_cast<uint32_t*>(dSs + (r0 + 8) * LDS + c0) = pack_bf16x2(ds[2], ds[3]);
+        }
+    }
+    __syncthreads();
+    // one gradient at a time: acc(16 rows x 64) = A^T-or-A (from Ps / dSs) * B (from dOs / Qs / Ks)
+    auto store_rows = [&](const float (&acc)[8][4], int col_off, float mul) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int pos = warp * 16 + g + r * 8;
+            if (pos >= T) continue;
+            bf16* p = dbase + static_cast<int64_t>(pos) * ld + col_off;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+                *reinterpret_cast<uint32_t*>(p + nt * 8 + 2 * t4) = pack_bf16x2(acc[nt][2 * r] * mul, acc[nt][2 * r + 1] * mul);
+        }
+    };
+    {   // dV = P^T dO
+        float acc[8][4];
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[x][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a[4];
+            load_a_trans(a, Ps, warp * 16, ks * 16, lane);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t bfr[4];
+                load_b_trans(bfr, dOs, np * 16, ks * 16, lane);
+                mma_bf16(acc[2 * np], a, bfr[0], bfr[1]);
+                mma_bf16(acc[2 * np + 1], a, bfr[2], bfr[3]);
+            }
+        }
+        store_rows(acc, 2 * d, 1.0f);
+    }
+    {   // dK = dS^T Q
+        float acc[8][4];
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[x][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a[4];
+            load_a_trans(a, dSs, warp * 16, ks * 16, lane);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t bfr[4];
+                load_b_trans(bfr, Qs, np * 16, ks * 16, lane);
+                mma_bf16(acc[2 * np], a, bfr[0], bfr[1]);
+                mma_bf16(acc[2 * np + 1], a, bfr[2], bfr[3]);
+            }
+        }
+        store_rows(acc, d, scale);
+    }
+    {   // dQ = dS K
+        float acc[8][4];
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[x][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a[4];
+            load_a(a, dSs, warp * 16, ks * 16, lane);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t bfr[4];
+                load_b_trans(bfr, Ks, np * 16, ks * 16, lane);
+                mma_bf16(acc[2 * np], a, bfr[0], bfr[1]);
+                mma_bf16(acc[2 * np + 1], a, bfr[2], bfr[3]);
+            }
+        }
+        store_rows(acc, 0, scale);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ KV cache / decode
 __global__ void kv_cache_fill_kernel(const uint4* __restrict__ qkv, uint4* __restrict__ cache, int B, int T, int Tmax,
                                      int d8) {
@@ -468,6 +632,255 @@ __global__ void __launch_bounds__(128) lm_attention_decode_kernel(const bf16* __
         }
     }
     *reinterpret_cast<uint32_t*>(o + static_cast<int64_t>(b) * d + h * HD + 2 * lane) = pack_bf16x2(a0 * inv, a1 * inv);
+}
+
+// ------------------------------------------------------------------------------------------ mapper attention, tensor-core path
+// S <= 32, head_dim in {16, 32, 64, 96, 128}: one 64-thread CTA per (sample, head), warp w owns query rows 16w..16w+15
+// (and, in the backward, key rows 16w..).  bf16 mma.sync with fp32 softmax; replaces the shared-memory-bound scalar
+// kernels below (round-1 profile: 67 us forward / 131 us backward per layer for 0.3 GFLOP of work).
+template <int LD> __device__ __forceinline__ void ld_a(uint32_t (&a)[4], const bf16* tile, int row0, int k0, int lane) {
+    const int mi = lane >> 3, r = lane & 7;
+    ldmatrix_x4(a, smem_addr(tile + (row0 + (mi & 1) * 8 + r) * LD + k0 + (mi >> 1) * 8));
+}
+template <int LD> __device__ __forceinline__ void ld_a_trans(uint32_t (&a)[4], const bf16* tile, int m0, int k0, int lane) {
+    const int mi = lane >> 3, r = lane & 7;
+    ldmatrix_x4_trans(a, smem_addr(tile + (k0 + (mi >> 1) * 8 + r) * LD + m0 + (mi & 1) * 8));
+}
+template <int LD> __device__ __forceinline__ void ld_b(uint32_t (&b)[4], const bf16* tile, int n0, int k0, int lane) {
+    const int mi = lane >> 3, r = lane & 7;
+    ldmatrix_x4(b, smem_addr(tile + (n0 + (mi >> 1) * 8 + r) * LD + k0 + (mi & 1) * 8));
+}
+template <int LD> __device__ __forceinline__ void ld_b_trans(uint32_t (&b)[4], const bf16* tile, int n0, int k0, int lane) {
+    const int mi = lane >> 3, r = lane & 7;
+    ldmatrix_x4_trans(b, smem_addr(tile + (k0 + (mi & 1) * 8 + r) * LD + n0 + (mi >> 1) * 8));
+}
+
+template <int HDIM>
+__device__ __forceinline__ void load_rows32(bf16* dst, const bf16* src, int64_t ld, int S, int tid) {
+    constexpr int LD = HDIM + 8, CPR = HDIM / 8;
+    for (int idx = tid; idx < 32 * CPR; idx += 64) {
+        const int r = idx / CPR, c = (idx % CPR) * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < S) v = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r) * ld + c);
+        *reinterpret_cast<uint4*>(dst + r * LD + c) = v;
+    }
+}
+
+// scores of this warp's 16 queries against 32 keys: acc[4][4]
+template <int HDIM>
+__device__ __forceinline__ void scores32(float (&acc)[4][4], const bf16* As, const bf16* Bs, int warp, int lane) {
+    constexpr int LD = HDIM + 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < HDIM / 16; ++ks) {
+        uint32_t a[4];
+        ld_a<LD>(a, As, warp * 16, ks * 16, lane);
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            uint32_t b[4];
+            ld_b<LD>(b, Bs, np * 16, ks * 16, lane);
+            mma_bf16(acc[2 * np], a, b[0], b[1]);
+            mma_bf16(acc[2 * np + 1], a, b[2], b[3]);
+        }
+    }
+}
+
+template <int HDIM>
+__global__ void __launch_bounds__(64) mapper_attention_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int S, int H) {
+    constexpr int LD = HDIM + 8;
+    __shared__ __align__(16) bf16 Qs[32 * LD];
+    __shared__ __align__(16) bf16 Ks[32 * LD];
+    __shared__ __align__(16) bf16 Vs[32 * LD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int d = H * HDIM;
+    const int64_t ld = 3 * d;
+    const bf16* base = qkv + static_cast<int64_t>(b) * S * ld + h * HDIM;
+    load_rows32<HDIM>(Qs, base, ld, S, tid);
+    load_rows32<HDIM>(Ks, base + d, ld, S, tid);
+    load_rows32<HDIM>(Vs, base + 2 * d, ld, S, tid);
+    __syncthreads();
+    float sacc[4][4];
+    scores32<HDIM>(sacc, Qs, Ks, warp, lane);
+    const float scale = rsqrtf(static_cast<float>(HDIM));      // clipcap.py:75
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int col = nt * 8 + 2 * t4 + (e & 1);
+            const float v = col < S ? sacc[nt][e] * scale : -INFINITY;
+            sacc[nt][e] = v;
+            mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float p = __expf(sacc[nt][e] - mx[e >> 1]);
+            sacc[nt][e] = p;
+            sum[e >> 1] += p;
+        }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+        sum[r] = 1.0f / sum[r];
+    }
+    uint32_t pf[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(sacc[nt][0] * sum[0], sacc[nt][1] * sum[0]);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(sacc[nt][2] * sum[1], sacc[nt][3] * sum[1]);
+    }
+    float oacc[HDIM / 8][4];
+#pragma unroll
+    for (int i = 0; i < HDIM / 8; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oacc[i][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int np = 0; np < HDIM / 16; ++np) {
+            uint32_t bfr[4];
+            ld_b_trans<LD>(bfr, Vs, np * 16, ks * 16, lane);
+            mma_bf16(oacc[2 * np], pf[ks], bfr[0], bfr[1]);
+            mma_bf16(oacc[2 * np + 1], pf[ks], bfr[2], bfr[3]);
+        }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int q = warp * 16 + g + r * 8;
+        if (q >= S) continue;
+        bf16* op = o + (static_cast<int64_t>(b) * S + q) * d + h * HDIM;
+#pragma unroll
+        for (int nt = 0; nt < HDIM / 8; ++nt)
+            *reinterpret_cast<uint32_t*>(op + nt * 8 + 2 * t4) = pack_bf16x2(oacc[nt][2 * r], oacc[nt][2 * r + 1]);
+    }
+}
+
+template <int HDIM>
+__global__ void __launch_bounds__(64) mapper_attention_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
+                                                                      bf16* __restrict__ dqkv, int S, int H) {
+    constexpr int LD = HDIM + 8, LP = 40;
+    extern __shared__ __align__(16) uint8_t smem_map[];
+    bf16* Qs = reinterpret_cast<bf16*>(smem_map);
+    bf16* Ks = Qs + 32 * LD;
+    bf16* Vs = Ks + 32 * LD;
+    bf16* Gs = Vs + 32 * LD;
+    bf16* Ps = Gs + 32 * LD;
+    bf16* dSs = Ps + 32 * LP;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int d = H * HDIM;
+    const int64_t ld = 3 * d;
+    const bf16* base = qkv + static_cast<int64_t>(b) * S * ld + h * HDIM;
+    bf16* dbase = dqkv + static_cast<int64_t>(b) * S * ld + h * HDIM;
+    load_rows32<HDIM>(Qs, base, ld, S, tid);
+    load_rows32<HDIM>(Ks, base + d, ld, S, tid);
+    load_rows32<HDIM>(Vs, base + 2 * d, ld, S, tid);
+    load_rows32<HDIM>(Gs, d_o + static_cast<int64_t>(b) * S * d + h * HDIM, d, S, tid);
+    __syncthreads();
+    const float scale = rsqrtf(static_cast<float>(HDIM));
+    {
+        float sacc[4][4], dpacc[4][4];
+        scores32<HDIM>(sacc, Qs, Ks, warp, lane);       // S  = Q K^T
+        scores32<HDIM>(dpacc, Gs, Vs, warp, lane);      // dP = dO V^T
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = nt * 8 + 2 * t4 + (e & 1);
+                const float v = col < S ? sacc[nt][e] * scale : -INFINITY;
+                sacc[nt][e] = v;
+                mx[e >> 1] = fmaxf(mx[e >> 1], v);
+            }
+        float sum[2] = {0.f, 0.f}, dot[2] = {0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float p = __expf(sacc[nt][e] - mx[e >> 1]);
+                sacc[nt][e] = p;
+                sum[e >> 1] += p;
+                dot[e >> 1] += p * dpacc[nt][e];
+            }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+            sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+            dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], 1);
+            dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], 2);
+            sum[r] = 1.0f / sum[r];
+            dot[r] *= sum[r];                            // sum_j p_ij dP_ij with normalised p
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float p[4], ds[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int row = warp * 16 + g + ((e >> 1) << 3);
+                p[e] = row < S ? sacc[nt][e] * sum[e >> 1] : 0.f;      // padded query rows must not reach dK / dV
+                ds[e] = p[e] * (dpacc[nt][e] - dot[e >> 1]) * scale;
+            }
+            const int r0 = warp * 16 + g, c0 = nt * 8 + 2 * t4;
+            *reinterpret_cast<uint32_t*>(Ps + r0 * LP + c0) = pack_bf16x2(p[0], p[1]);
+            *reinterpret_cast<uint32_t*>(Ps + (r0 + 8) * LP + c0) = pack_bf16x2(p[2], p[3]);
+            *reinterpret_cast<uint32_t*>(dSs + r0 * LP + c0) = pack_bf16x2(ds[0], ds[1]);
+            *reinterpret_cast<uint32_t*>(dSs + (r0 + 8) * LP + c0) = pack_bf16x2(ds[2], ds[3]);
+        }
+    }
+    __syncthreads();
+    auto store_rows = [&](const float (&acc)[HDIM / 8][4], int col_off) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int pos = warp * 16 + g + r * 8;
+            if (pos >= S) continue;
+            bf16* p = dbase + static_cast<int64_t>(pos) * ld + col_off;
+#pragma unroll
+            for (int nt = 0; nt < HDIM / 8; ++nt)
+                *reinterpret_cast<uint32_t*>(p + nt * 8 + 2 * t4) = pack_bf16x2(acc[nt][2 * r], acc[nt][2 * r + 1]);
+        }
+    };
+    // which: 0 -> dV = P^T dO, 1 -> dK = dS^T Q (A transposed from smem), 2 -> dQ = dS K
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+        float acc[HDIM / 8][4];
+#pragma unroll
+        for (int i = 0; i < HDIM / 8; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+        const bf16* Asrc = which == 0 ? Ps : dSs;
+        const bf16* Bsrc = which == 0 ? Gs : (which == 1 ? Qs : Ks);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t a[4];
+            if (which == 2) ld_a<LP>(a, Asrc, warp * 16, ks * 16, lane);
+            else ld_a_trans<LP>(a, Asrc, warp * 16, ks * 16, lane);
+#pragma unroll
+            for (int np = 0; np < HDIM / 16; ++np) {
+                uint32_t bfr[4];
+                ld_b_trans<LD>(bfr, Bsrc, np * 16, ks * 16, lane);
+                mma_bf16(acc[2 * np], a, bfr[0], bfr[1]);
+                mma_bf16(acc[2 * np + 1], a, bfr[2], bfr[3]);
+            }
+        }
+        store_rows(acc, which == 0 ? 2 * d : (which == 1 ? d : 0));
+    }
 }
 
 // ------------------------------------------------------------------------------------------ mapper attention
@@ -618,6 +1031,17 @@ void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf
     }
     EAVQA_CHECK(T <= BLK || dq_scratch != nullptr, "lm_attention_bwd needs dq_scratch for T > 64");
     dim3 grid(H, B);
+    if (T <= BLK) {
+        static bool configured1 = false;
+        if (!configured1) {
+            CUDA_CHECK(cudaFuncSetAttribute(lm_attention_bwd_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured1 = true;
+        }
+        lm_attention_bwd_single_kernel<<<grid, 128, smem, s>>>(qkv, valid, o, d_o, lse, dqkv, T, H);
+        KERNEL_CHECK();
+        count_launch();
+        return;
+    }
     lm_attention_bwd_kernel<<<grid, 128, smem, s>>>(qkv, valid, o, d_o, lse, dqkv, dq_scratch, T, H);
     KERNEL_CHECK();
     count_launch();
@@ -643,7 +1067,31 @@ void lm_attention_decode(const bf16* qkv_new, bf16* cache, const int* valid, int
     count_launch();
 }
 
+template <int HDIM>
+static void launch_mapper_bwd_mma(const bf16* qkv, const bf16* d_o, bf16* dqkv, int B, int S, int H, cudaStream_t s) {
+    const int smem = (4 * 32 * (HDIM + 8) + 2 * 32 * 40) * sizeof(bf16);
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        CUDA_CHECK(cudaFuncSetAttribute(mapper_attention_bwd_mma_kernel<HDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    mapper_attention_bwd_mma_kernel<HDIM><<<dim3(H, B), 64, smem, s>>>(qkv, d_o, dqkv, S, H);
+}
+
 void mapper_attention_fwd(const bf16* qkv, bf16* o, int B, int S, int H, int hd, cudaStream_t s) {
+    if (S <= 32 && (hd == 16 || hd == 32 || hd == 64 || hd == 96 || hd == 128)) {
+        dim3 grid(H, B);
+        switch (hd) {
+            case 16: mapper_attention_fwd_mma_kernel<16><<<grid, 64, 0, s>>>(qkv, o, S, H); break;
+            case 32: mapper_attention_fwd_mma_kernel<32><<<grid, 64, 0, s>>>(qkv, o, S, H); break;
+            case 64: mapper_attention_fwd_mma_kernel<64><<<grid, 64, 0, s>>>(qkv, o, S, H); break;
+            case 96: mapper_attention_fwd_mma_kernel<96><<<grid, 64, 0, s>>>(qkv, o, S, H); break;
+            default: mapper_attention_fwd_mma_kernel<128><<<grid, 64, 0, s>>>(qkv, o, S, H); break;
+        }
+        KERNEL_CHECK();
+        count_launch();
+        return;
+    }
     const int smem = (3 * S * (hd + 1) + S * (S + 1)) * sizeof(float);
     EAVQA_CHECK(smem <= 200 * 1024, "mapper attention tile does not fit in shared memory");
     static int configured = 0;
@@ -658,6 +1106,18 @@ void mapper_attention_fwd(const bf16* qkv, bf16* o, int B, int S, int H, int hd,
 }
 
 void mapper_attention_bwd(const bf16* qkv, const bf16* d_o, bf16* dqkv, int B, int S, int H, int hd, cudaStream_t s) {
+    if (S <= 32 && (hd == 16 || hd == 32 || hd == 64 || hd == 96 || hd == 128)) {
+        switch (hd) {
+            case 16: launch_mapper_bwd_mma<16>(qkv, d_o, dqkv, B, S, H, s); break;
+            case 32: launch_mapper_bwd_mma<32>(qkv, d_o, dqkv, B, S, H, s); break;
+            case 64: launch_mapper_bwd_mma<64>(qkv, d_o, dqkv, B, S, H, s); break;
+            case 96: launch_mapper_bwd_mma<96>(qkv, d_o, dqkv, B, S, H, s); break;
+            default: launch_mapper_bwd_mma<128>(qkv, d_o, dqkv, B, S, H, s); break;
+        }
+        KERNEL_CHECK();
+        count_launch();
+        return;
+    }
     const int smem = (4 * S * (hd + 1) + 2 * S * (S + 1)) * sizeof(float);
     EAVQA_CHECK(smem <= 200 * 1024, "mapper attention tile does not fit in shared memory");
     static int configured = 0;

@@ -231,6 +231,118 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
     }
 }
 
+// Frozen-LM / dx-only LayerNorm backward, tuned for occupancy (round-1 ncu: the fused variant used 103 registers ->
+// 2 CTAs/SM, 28 % of DRAM peak).  x and dy stay in registers (x fp32, dy packed bf16); xhat and gamma*dy are
+// recomputed in the second sweep instead of being kept.
+template <int MAXV>
+__global__ void __launch_bounds__(256, (MAXV <= 6) ? 4 : (MAXV <= 10) ? 3 : 2) layernorm_bwd_lean_kernel(const bf16* __restrict__ dy, int ld_dy,
+                                                                    const float* __restrict__ x, int ld_x,
+                                                                    const int* __restrict__ row_index,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ mean_in,
+                                                                    const float* __restrict__ rstd_in, float* __restrict__ dx,
+                                                                    int ld_dx, int accumulate, bf16* __restrict__ dx_bf16,
+                                                                    int ld_dxb, int M, int d) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (m >= M) return;
+    const int n4 = d >> 2;
+    const int xr = row_index ? row_index[m] : m;
+    const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(xr) * ld_x);
+    const uint2* dyp = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(m) * ld_dy);
+    const float4* gp = reinterpret_cast<const float4*>(gamma);
+    const float mean = mean_in[m], rstd = rstd_in[m];
+    float4 xv[MAXV];
+    uint2 dv[MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < n4) {
+            xv[i] = xp[c];
+            dv[i] = dyp[c];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < n4) {
+            const float4 gm = __ldg(gp + c);
+            const float2 d0 = unpack_bf16x2(dv[i].x), d1 = unpack_bf16x2(dv[i].y);
+            const float g0 = d0.x * gm.x, g1 = d0.y * gm.y, g2 = d1.x * gm.z, g3 = d1.y * gm.w;
+            s1 += g0 + g1 + g2 + g3;
+            s2 += g0 * (xv[i].x - mean) + g1 * (xv[i].y - mean) + g2 * (xv[i].z - mean) + g3 * (xv[i].w - mean);
+        }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) * rstd / d;
+    float4* dxp = reinterpret_cast<float4*>(dx + static_cast<size_t>(xr) * ld_dx);
+    uint2* dbp = dx_bf16 ? reinterpret_cast<uint2*>(dx_bf16 + static_cast<size_t>(xr) * ld_dxb) : nullptr;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < n4) {
+            const float4 gm = __ldg(gp + c);
+            const float2 d0 = unpack_bf16x2(dv[i].x), d1 = unpack_bf16x2(dv[i].y);
+            float4 r;
+            r.x = rstd * (d0.x * gm.x - s1 - (xv[i].x - mean) * rstd * s2);
+            r.y = rstd * (d0.y * gm.y - s1 - (xv[i].y - mean) * rstd * s2);
+            r.z = rstd * (d1.x * gm.z - s1 - (xv[i].z - mean) * rstd * s2);
+            r.w = rstd * (d1.y * gm.w - s1 - (xv[i].w - mean) * rstd * s2);
+            if (accumulate) {
+                const float4 o = dxp[c];
+                r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+            }
+            dxp[c] = r;
+            if (dbp) {
+                uint2 o;
+                o.x = pack_bf16x2(r.x, r.y);
+                o.y = pack_bf16x2(r.z, r.w);
+                dbp[c] = o;
+            }
+        }
+    }
+}
+
+// column reduction over rows: block = 32 column-pairs x 8 row lanes, 256 rows per block
+__global__ void __launch_bounds__(256) ln_param_grad_kernel(const bf16* __restrict__ dy, int ld_dy, const float* __restrict__ x,
+                                                            int ld_x, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int M, int d) {
+    __shared__ float sg[8][64], sb[8][64];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int c = blockIdx.x * 64 + 2 * tx;
+    const int r0 = blockIdx.y * 256;
+    float g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
+    if (c < d) {
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int r = r0 + ty + 8 * i;
+            if (r < M) {
+                const float2 dv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + static_cast<size_t>(r) * ld_dy + c));
+                const float2 xv = *reinterpret_cast<const float2*>(x + static_cast<size_t>(r) * ld_x + c);
+                const float mu = mean[r], rs = rstd[r];
+                g0 += dv.x * (xv.x - mu) * rs;
+                g1 += dv.y * (xv.y - mu) * rs;
+                b0 += dv.x;
+                b1 += dv.y;
+            }
+        }
+    }
+    sg[ty][2 * tx] = g0; sg[ty][2 * tx + 1] = g1;
+    sb[ty][2 * tx] = b0; sb[ty][2 * tx + 1] = b1;
+    __syncthreads();
+    if (ty == 0 && c < d) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
+            g0 += sg[i][2 * tx]; g1 += sg[i][2 * tx + 1];
+            b0 += sb[i][2 * tx]; b1 += sb[i][2 * tx + 1];
+        }
+        atomicAdd(dgamma + c, g0); atomicAdd(dgamma + c + 1, g1);
+        atomicAdd(dbeta + c, b0); atomicAdd(dbeta + c + 1, b1);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ embedding / splice
 __global__ void prepend_plan_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ mask, int B, int Tt,
                                     int P, int* __restrict__ plan, int* __restrict__ valid) {
@@ -559,12 +671,15 @@ void layernorm_fwd(const float* x, int ld_x, const int* row_index, const float* 
     EAVQA_CHECK(d % 4 == 0 && d <= 2048 && ld_x % 4 == 0 && ld_y % 4 == 0, "layernorm width must be a multiple of 4 and <= 2048");
     const int need = ceil_div(d / 4, 32);
     const int grid = ceil_div(M, 8);
-    if (need <= 4)
-        layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, ld_x, row_index, gamma, beta, y, ld_y, mean, rstd, M, d, eps);
-    else if (need <= 8)
-        layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, ld_x, row_index, gamma, beta, y, ld_y, mean, rstd, M, d, eps);
-    else
-        layernorm_fwd_kernel<16><<<grid, 256, 0, s>>>(x, ld_x, row_index, gamma, beta, y, ld_y, mean, rstd, M, d, eps);
+#define EAVQA_LN_FWD(V) layernorm_fwd_kernel<V><<<grid, 256, 0, s>>>(x, ld_x, row_index, gamma, beta, y, ld_y, mean, rstd, M, d, eps)
+    if (need <= 2) EAVQA_LN_FWD(2);
+    else if (need <= 4) EAVQA_LN_FWD(4);
+    else if (need <= 6) EAVQA_LN_FWD(6);
+    else if (need <= 8) EAVQA_LN_FWD(8);
+    else if (need <= 10) EAVQA_LN_FWD(10);
+    else if (need <= 13) EAVQA_LN_FWD(13);
+    else EAVQA_LN_FWD(16);
+#undef EAVQA_LN_FWD
     KERNEL_CHECK();
     count_launch();
 }
@@ -573,15 +688,21 @@ template <int MAXV>
 static void launch_ln_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, const int* row_index, const float* gamma,
                           const float* mean, const float* rstd, float* dx, int ld_dx, int accumulate, bf16* dx_bf16,
                           int ld_dxb, float* dgamma, float* dbeta, int M, int d, cudaStream_t s) {
-    if (dgamma != nullptr) {
+    if (dgamma != nullptr && row_index != nullptr) {
+        // gathered rows + parameter gradients: not on the step's path; keep the fused (register-heavy) variant
         const int grid = std::min(ceil_div(M, 8), 2 * num_sms());
         layernorm_bwd_kernel<MAXV, true><<<grid, 256, 2 * d * sizeof(float), s>>>(
             dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx, accumulate, dx_bf16, ld_dxb, dgamma, dbeta, M, d);
-    } else {
-        const int grid = ceil_div(M, 8);
-        layernorm_bwd_kernel<MAXV, false><<<grid, 256, 0, s>>>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx,
-                                                               ld_dx, accumulate, dx_bf16, ld_dxb, nullptr, nullptr, M, d);
+        KERNEL_CHECK();
+        count_launch();
+        return;
     }
+    // the 157-register fused variant ran at one CTA per SM (round-1 profile: 47 us for 63 MB); the column reduction
+    // re-reads dy and x (L2-resident) in a second, occupancy-friendly kernel instead
+    if (dgamma != nullptr) layernorm_param_grads(dy, ld_dy, x, ld_x, mean, rstd, dgamma, dbeta, M, d, s);
+    const int grid = ceil_div(M, 8);
+    layernorm_bwd_lean_kernel<MAXV><<<grid, 256, 0, s>>>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx,
+                                                         accumulate, dx_bf16, ld_dxb, M, d);
     KERNEL_CHECK();
     count_launch();
 }
@@ -593,12 +714,24 @@ void layernorm_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, const in
     EAVQA_CHECK(mean != nullptr && rstd != nullptr, "layernorm_bwd needs the saved statistics");
     EAVQA_CHECK((dgamma == nullptr) == (dbeta == nullptr), "dgamma and dbeta go together");
     const int need = ceil_div(d / 4, 32);
-    if (need <= 4)
-        launch_ln_bwd<4>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx, accumulate, dx_bf16, ld_dxb, dgamma, dbeta, M, d, s);
-    else if (need <= 8)
-        launch_ln_bwd<8>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx, accumulate, dx_bf16, ld_dxb, dgamma, dbeta, M, d, s);
-    else
-        launch_ln_bwd<16>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx, accumulate, dx_bf16, ld_dxb, dgamma, dbeta, M, d, s);
+#define EAVQA_LN_BWD(V) launch_ln_bwd<V>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx, accumulate, dx_bf16, ld_dxb, dgamma, dbeta, M, d, s)
+    if (need <= 2) EAVQA_LN_BWD(2);
+    else if (need <= 4) EAVQA_LN_BWD(4);
+    else if (need <= 6) EAVQA_LN_BWD(6);          // d = 768
+    else if (need <= 8) EAVQA_LN_BWD(8);          // d = 1024
+    else if (need <= 10) EAVQA_LN_BWD(10);        // d = 1280
+    else if (need <= 13) EAVQA_LN_BWD(13);        // d = 1600
+    else EAVQA_LN_BWD(16);
+#undef EAVQA_LN_BWD
+}
+
+void layernorm_param_grads(const bf16* dy, int ld_dy, const float* x, int ld_x, const float* mean, const float* rstd,
+                           float* dgamma, float* dbeta, int M, int d, cudaStream_t s) {
+    EAVQA_CHECK(d % 2 == 0 && ld_dy % 2 == 0 && ld_x % 2 == 0, "layernorm_param_grads alignment");
+    dim3 grid(ceil_div(d, 64), ceil_div(M, 256)), block(32, 8);
+    ln_param_grad_kernel<<<grid, block, 0, s>>>(dy, ld_dy, x, ld_x, mean, rstd, dgamma, dbeta, M, d);
+    KERNEL_CHECK();
+    count_launch();
 }
 
 void prepend_plan(const int64_t* tokens, const int64_t* mask, int B, int Tt, int P, int* plan, int* valid, cudaStream_t s) {

@@ -31,6 +31,10 @@ void layernorm_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, const in
                    const float* mean, const float* rstd, float* dx, int ld_dx, int accumulate, bf16* dx_bf16,
                    int ld_dxb, float* dgamma, float* dbeta, int M, int d, float eps, cudaStream_t s);
 
+// dgamma[c] += sum_m dy[m,c] * xhat[m,c],  dbeta[c] += sum_m dy[m,c]   (trainable mapper LayerNorms; atomicAdd)
+void layernorm_param_grads(const bf16* dy, int ld_dy, const float* x, int ld_x, const float* mean, const float* rstd,
+                           float* dgamma, float* dbeta, int M, int d, cudaStream_t s);
+
 // ---------------------------------------------------------------- embedding / splice (elementwise.cu)
 // plan[b, t] >= 0 : token id ; < 0 : -(prefix_row + 1) ; valid[b, t] = key-validity (attention mask)
 void prepend_plan(const int64_t* tokens, const int64_t* mask, int B, int Tt, int P, int* plan, int* valid, cudaStream_t s);
