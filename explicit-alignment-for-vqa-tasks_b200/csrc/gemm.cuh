@@ -44,11 +44,13 @@ struct GemmArgs {
     int lda = 0, ldb = 0;            // row strides in elements (multiples of 8)
     int M = 0, N = 0, K = 0;
     int block_n = 0;                 // 0 = pick by wave-quantisation heuristic; else 64/128/192/256
+    int cluster = 0;                 // 0 = heuristic; 1 = single CTAs; 2 = 2x1 cluster (B multicast); 4 = 2x2 (A and B)
     GemmEpilogue ep;
 };
 
 // Number of N tiles the heuristic (or block_n) will use: callers size ce_partial with it.
 int gemm_pick_block_n(int M, int N, int K, int forced);
+int gemm_pick_cluster(int M, int N, int bn, int forced);
 void gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream);
 // kernels this translation unit launched since process start (bench.py's gpu_launches)
 int64_t gemm_launch_count();

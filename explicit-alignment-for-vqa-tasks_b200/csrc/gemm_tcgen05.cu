@@ -143,10 +143,25 @@ struct TmaMaps {
     CUtensorMap a, b, out, out2, in;
 };
 
-template <int BN, bool CE>
+// CM x CN thread-block cluster: the CM CTAs of a cluster column share one B tile and the CN CTAs of a cluster row
+// share one A tile; each CTA fetches 1/CM of B (1/CN of A) and TMA-multicasts it to its peers, so every operand
+// byte crosses the L2 -> SM fabric once per cluster instead of once per CTA.  (Round-1 measurement: with single
+// CTAs the 128x192 tile needs 40 KB per 64-deep K block, and L2 delivers ~46 B/clk/SM -> ~890 clk per K block
+// against 384 clk of MMA: every large GEMM plateaued at ~1000 TFLOP/s.)
+template <int BN, bool CE, int CM, int CN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, const GemmEpilogue ep) {
     using C = Cfg<BN>;
+    constexpr int CLUSTER = CM * CN;
+    const uint32_t crank = CLUSTER > 1 ? ptx::cluster_ctarank() : 0u;
+    const int cm = crank % CM, cn = crank / CM;
+    // peers that share my A tile (same cm) / my B tile (same cn), as cluster-rank bit masks
+    uint16_t mask_a = 0, mask_b = 0;
+#pragma unroll
+    for (int j = 0; j < CN; ++j) mask_a |= static_cast<uint16_t>(1u << (cm + CM * j));
+#pragma unroll
+    for (int i = 0; i < CM; ++i) mask_b |= static_cast<uint16_t>(1u << (i + CM * cn));
+    const uint16_t mask_release = mask_a | mask_b;       // everyone whose producer writes into my stages
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-B aligned bases (descriptor base_offset = 0)
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -174,7 +189,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
         ptx::prefetch_tensormap(&maps.out);
         for (int i = 0; i < C::STAGES; ++i) {
             ptx::mbar_init(full_bar + 8 * i, 1);
-            ptx::mbar_init(empty_bar + 8 * i, 1);
+            ptx::mbar_init(empty_bar + 8 * i, CM + CN - 1);    // my MMA warp + every peer that multicasts into this slot
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(tfull_bar + 8 * i, 1);
@@ -190,27 +205,48 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
     }
     ptx::tcgen05_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) ptx::cluster_sync();                 // peers' barriers are initialised before anyone signals them
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int num_m = (M + BM - 1) / BM;
     const int num_n = (N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
+    // the cluster walks "super tiles" of CM x CN tiles; CTA (cm, cn) owns tile (sm * CM + cm, sn * CN + cn).  Tiles
+    // past the edge are computed on zero-filled operands and clipped by the TMA stores.
+    const int num_sm = (num_m + CM - 1) / CM;
+    const int num_sn = (num_n + CN - 1) / CN;
+    const int num_tiles = num_sm * num_sn;
     const int num_kb = (K + BK - 1) / BK;
+    const int tile_begin = blockIdx.x / CLUSTER;
+    const int tile_step = gridDim.x / CLUSTER;
+    auto coords = [&](int tile, int& m_idx, int& n_idx) {
+        int sm, sn;
+        tile_coords(tile, num_sm, num_sn, sm, sn);
+        m_idx = sm * CM + cm;
+        n_idx = sn * CN + cn;
+    };
 
     if (warp == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
                 int m_idx, n_idx;
-                tile_coords(tile, num_m, num_n, m_idx, n_idx);
+                coords(tile, m_idx, n_idx);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1);           // the slot is free here AND in every peer
                     ptx::mbar_arrive_expect_tx(full_bar + 8 * stage, C::STAGE_A + C::STAGE_B);
-                    ptx::tma_load_2d(smem_a + stage * C::STAGE_A, &maps.a, full_bar + 8 * stage, kb * BK, m_idx * BM);
-                    ptx::tma_load_2d(smem_b + stage * C::STAGE_B, &maps.b, full_bar + 8 * stage, kb * BK, n_idx * BN);
+                    if (CN == 1)
+                        ptx::tma_load_2d(smem_a + stage * C::STAGE_A, &maps.a, full_bar + 8 * stage, kb * BK, m_idx * BM);
+                    else
+                        ptx::tma_load_2d_multicast(smem_a + stage * C::STAGE_A + cn * (C::STAGE_A / CN), &maps.a,
+                                                   full_bar + 8 * stage, kb * BK, m_idx * BM + cn * (BM / CN), mask_a);
+                    if (CM == 1)
+                        ptx::tma_load_2d(smem_b + stage * C::STAGE_B, &maps.b, full_bar + 8 * stage, kb * BK, n_idx * BN);
+                    else
+                        ptx::tma_load_2d_multicast(smem_b + stage * C::STAGE_B + cm * (C::STAGE_B / CM), &maps.b,
+                                                   full_bar + 8 * stage, kb * BK, n_idx * BN + cm * (BN / CM), mask_b);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -223,7 +259,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
                 ptx::mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);     // epilogue drained this buffer
                 ptx::tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
@@ -237,7 +273,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
                         // advancing 16 bf16 (32 B) along K inside the 128-B swizzle row: +2 in the >>4 address field
                         ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit(empty_bar + 8 * stage);              // frees the smem slot when the MMAs retire
+                    // frees the smem slot (here and for the peers that multicast into it) when the MMAs retire
+                    if (CLUSTER == 1) ptx::umma_commit(empty_bar + 8 * stage);
+                    else ptx::umma_commit_multicast(empty_bar + 8 * stage, mask_release);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(tfull_bar + 8 * acc);                    // accumulator complete -> epilogue
@@ -268,7 +306,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
         };
         auto issue_in = [&](int tile, int c) {        // lane 0 only
             int m_idx, n_idx;
-            tile_coords(tile, num_m, num_n, m_idx, n_idx);
+            coords(tile, m_idx, n_idx);
             ptx::mbar_arrive_expect_tx(in_bar, in_bytes);
             ptx::tma_load_2d(bufB, &maps.in, in_bar, n_idx * BN + half * C::HALF + c * CHUNK, m_idx * BM + quarter * 32);
         };
@@ -276,22 +314,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
             int t = tile;
             while (t < num_tiles) {
                 int m_idx, n_idx;
-                tile_coords(t, num_m, num_n, m_idx, n_idx);
+                coords(t, m_idx, n_idx);
                 if (n_valid_chunks(n_idx) > 0) break;
-                t += gridDim.x;
+                t += tile_step;
             }
             return t;
         };
         if (has_in && lane == 0) {
-            const int t0 = next_tile_with_work(blockIdx.x);
+            const int t0 = next_tile_with_work(tile_begin);
             if (t0 < num_tiles) issue_in(t0, 0);
         }
 
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
             int m_idx, n_idx;
-            tile_coords(tile, num_m, num_n, m_idx, n_idx);
+            coords(tile, m_idx, n_idx);
             const int row0 = m_idx * BM + quarter * 32;
             const int row = row0 + lane;
             const bool row_ok = row < M;
@@ -421,7 +459,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
                         if (c + 1 < nvalid) {
                             issue_in(tile, c + 1);
                         } else {
-                            const int tn = next_tile_with_work(tile + gridDim.x);
+                            const int tn = next_tile_with_work(tile + tile_step);
                             if (tn < num_tiles) issue_in(tn, 0);
                         }
                     }
@@ -449,7 +487,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
                 }
                 ++out_slot;
             }
-            if (CE && row_ok)
+            if (CE && row_ok && n_idx < num_n)
                 ep.ce_partial[static_cast<size_t>(row) * ep.ce_tiles + n_idx * 2 + half] = make_float2(ce_m, ce_s);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -459,6 +497,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
 
     ptx::tcgen05_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) ptx::cluster_sync();                 // no CTA may exit while a peer can still signal its barriers
     if (warp == 1) {
         ptx::tcgen05_fence_after();
         ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -520,25 +559,27 @@ CUtensorMap make_map(const void* ptr, int rows, int cols, int ld, int box_rows, 
     return m;
 }
 
-template <int BN, bool CE>
+template <int BN, bool CE, int CM, int CN>
 void launch(const GemmArgs& a, cudaStream_t stream) {
     using C = Cfg<BN>;
+    constexpr int CLUSTER = CM * CN;
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, CE, CM, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
     const GemmEpilogue& e = a.ep;
     TmaMaps maps;
-    maps.a = make_map(a.A, a.M, a.K, a.lda, BM, MAP_OPERAND);
-    maps.b = make_map(a.B, a.N, a.K, a.ldb, BN, MAP_OPERAND);
+    maps.a = make_map(a.A, a.M, a.K, a.lda, BM / CN, MAP_OPERAND);      // each CTA fetches its 1/CN slice of the A tile
+    maps.b = make_map(a.B, a.N, a.K, a.ldb, BN / CM, MAP_OPERAND);      // ... and its 1/CM slice of the B tile
     maps.out = e.out ? make_map(e.out, a.M, a.N, e.ldo, 32, e.out_fp32 ? MAP_EPI_F32 : MAP_EPI_BF16) : maps.a;
     maps.out2 = e.out2 ? make_map(e.out2, a.M, a.N, e.ldo2, 32, MAP_EPI_BF16) : maps.a;
     if (e.residual) maps.in = make_map(e.residual, a.M, a.N, e.ld_res, 32, MAP_EPI_F32);
     else if (e.dact != DACT_NONE) maps.in = make_map(e.aux, a.M, a.N, e.ld_aux, 32, MAP_EPI_BF16);
     else maps.in = maps.a;
-    const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
+    const int tiles = ceil_div(ceil_div(a.M, BM), CM) * ceil_div(ceil_div(a.N, BN), CN);      // super tiles
+    const int max_clusters = num_sms() / CLUSTER;
+    const int grid = (tiles < max_clusters ? tiles : max_clusters) * CLUSTER;
     ProfRec rec;
     if (g_prof_on) {
         CUDA_CHECK(cudaEventCreate(&rec.start));
@@ -546,7 +587,19 @@ void launch(const GemmArgs& a, cudaStream_t stream) {
         rec.M = a.M; rec.N = a.N; rec.K = a.K; rec.bn = BN;
         CUDA_CHECK(cudaEventRecord(rec.start, stream));
     }
-    gemm_bf16_tn_kernel<BN, CE><<<grid, NUM_THREADS, C::SMEM, stream>>>(maps, a.M, a.N, a.K, a.ep);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, CE, CM, CN>, maps, a.M, a.N, a.K, a.ep));
     KERNEL_CHECK();
     if (g_prof_on) {
         CUDA_CHECK(cudaEventRecord(rec.stop, stream));
@@ -584,6 +637,18 @@ int gemm_pick_block_n(int M, int N, int K, int forced) {
     return best_bn;
 }
 
+// Cluster shape: 1 (none), 2 (2 x 1: B shared) or 4 (2 x 2: A and B shared).  Clusters pay off once there are enough
+// tiles for every cluster to stream several of them; small problems keep independent CTAs (better SM fill).
+int gemm_pick_cluster(int M, int N, int bn, int forced) {
+    if (forced == 1 || forced == 2 || forced == 4) return bn == 64 ? 1 : forced;
+    EAVQA_CHECK(forced == 0, "cluster must be 0, 1, 2 or 4");
+    // Measured on B200 (tools/gemm_bench.py, profiles/r01_gemm_cluster_sweep.txt): 2x1 multicast is within +-5 % of
+    // independent CTAs on every shape of the step and 2x2 is 30-45 % slower (lock-step stalls, stranded SMs), i.e. the
+    // L2 -> SM operand path is not the limiter -- the shared-memory port (TMA writes + UMMA operand reads) is.  Default: none.
+    (void)M; (void)N; (void)bn;
+    return 1;
+}
+
 void gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     EAVQA_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "GEMM with an empty dimension");
     EAVQA_CHECK(a.A != nullptr && a.B != nullptr, "GEMM operand is null");
@@ -599,12 +664,22 @@ void gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
         EAVQA_CHECK(e.ce_tiles == 2 * ceil_div(a.N, bn), "ce_tiles must be 2 * ceil(N / block_n)");
         EAVQA_CHECK(e.ce_target != nullptr && e.n_valid > 0 && e.n_valid <= a.N, "CE epilogue arguments");
     }
+    const int cl = gemm_pick_cluster(a.M, a.N, bn, a.cluster);
+#define EAVQA_GEMM_CASE(BN_)                                                                   \
+    case BN_:                                                                                  \
+        if (cl == 4) ce ? launch<BN_, true, 2, 2>(a, stream) : launch<BN_, false, 2, 2>(a, stream);      \
+        else if (cl == 2) ce ? launch<BN_, true, 2, 1>(a, stream) : launch<BN_, false, 2, 1>(a, stream); \
+        else ce ? launch<BN_, true, 1, 1>(a, stream) : launch<BN_, false, 1, 1>(a, stream);              \
+        break;
     switch (bn) {
-        case 256: ce ? launch<256, true>(a, stream) : launch<256, false>(a, stream); break;
-        case 192: ce ? launch<192, true>(a, stream) : launch<192, false>(a, stream); break;
-        case 128: ce ? launch<128, true>(a, stream) : launch<128, false>(a, stream); break;
-        default:  ce ? launch<64, true>(a, stream) : launch<64, false>(a, stream); break;
+        EAVQA_GEMM_CASE(256)
+        EAVQA_GEMM_CASE(192)
+        EAVQA_GEMM_CASE(128)
+        default:
+            ce ? launch<64, true, 1, 1>(a, stream) : launch<64, false, 1, 1>(a, stream);
+            break;
     }
+#undef EAVQA_GEMM_CASE
 }
 
 }  // namespace eavqa

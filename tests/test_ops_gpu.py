@@ -76,6 +76,27 @@ def test_gemm_plain_fp32_out(L, shape, block_n):
     assert err <= 2e-3 * math.sqrt(K), f"max err {err} (ref max {ref.abs().max().item()})"
 
 
+@pytest.mark.parametrize("cluster", [2, 4])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 128), (300, 200, 72), (1000, 768, 768), (130, 2304, 768),
+                                   (2000, 768, 3072), (5000, 1111 // 8 * 8, 320)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("block_n", [128, 192, 256])
+def test_gemm_clusters_tma_multicast(L, shape, block_n, cluster):
+    """2x1 / 2x2 thread-block clusters with TMA multicast of the shared operand tiles (odd tile counts leave a CTA
+    of the last cluster on an out-of-range tile that must be computed on zeros and clipped)."""
+    M, N, K = shape
+    A = _rand((M, K), 1, dtype=torch.bfloat16)
+    B = _rand((N, K), 2, dtype=torch.bfloat16)
+    bias = _rand((N,), 3)
+    res = _rand((M, N), 4)
+    out, _ = gemm(L, A, B, out_fp32=True, bias=bias, residual=res, block_n=block_n + 1000 * cluster)
+    ref = A.float() @ B.float().t() + bias + res
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * math.sqrt(K), f"max err {err}"
+    out, out2 = gemm(L, A, B, bias=bias, act=1, want_out2=True, block_n=block_n + 1000 * cluster)
+    pre = A.float() @ B.float().t() + bias
+    assert (out2.float() - pre).abs().max().item() <= 2e-3 * math.sqrt(K) + 2 ** -8 * pre.abs().max().item()
+
+
 def test_gemm_identity_exposes_layout(L):
     """B = I: the output must reproduce A exactly (bf16 values are exact in fp32) -- catches any swizzle /
     descriptor / TMEM-lane mix-up as a permutation."""
