@@ -162,14 +162,15 @@ int eavqa_op_gemm(const void* A, int32_t lda, const void* B, int32_t ldb, int32_
 int eavqa_op_lmhead_ce(const void* H, const void* W, int32_t M, int32_t vocab, int32_t n_cols, int32_t K, const int32_t* label,
                        void* logits, int32_t ldo, float* lse, float* target, float* loss_sum, void* stream) {
     API_BEGIN
-    const int bn = gemm_pick_block_n(M, n_cols, K, 0);
+    int bn = 0, cluster = 1;
+    gemm_pick_config(M, n_cols, K, 0, 0, &bn, &cluster);
     const int tiles = 2 * ceil_div(n_cols, bn);
     float2* partial = nullptr;
     CUDA_CHECK(cudaMalloc(&partial, sizeof(float2) * static_cast<size_t>(M) * tiles));
     try {
         GemmArgs a;
         a.A = static_cast<const bf16*>(H); a.lda = K; a.B = static_cast<const bf16*>(W); a.ldb = K;
-        a.M = M; a.N = n_cols; a.K = K; a.block_n = bn;
+        a.M = M; a.N = n_cols; a.K = K; a.block_n = bn; a.cluster = cluster;
         a.ep.out = logits; a.ep.ldo = ldo; a.ep.out_fp32 = 0;
         a.ep.ce_partial = partial; a.ep.ce_target = target; a.ep.ce_label = label; a.ep.ce_tiles = tiles; a.ep.n_valid = vocab;
         gemm_bf16_tn(a, S(stream));

@@ -86,6 +86,8 @@ __device__ __forceinline__ void warp_gemm_nt(float (&acc)[8][4], const uint32_t 
 __global__ void __launch_bounds__(128, 4) lm_attention_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
                                                                bf16* __restrict__ o, float* __restrict__ lse, int T,
                                                                int H) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) bf16 Qs[BLK * LDS];
     __shared__ __align__(16) bf16 Ks[BLK * LDS];
     __shared__ __align__(16) bf16 Vs[BLK * LDS];
@@ -200,6 +202,8 @@ __global__ void __launch_bounds__(128) lm_attention_bwd_kernel(const bf16* __res
                                                                const bf16* __restrict__ o, const bf16* __restrict__ d_o,
                                                                const float* __restrict__ lse, bf16* __restrict__ dqkv,
                                                                float* __restrict__ dq_scratch, int T, int H) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t smem_bwd[];
     bf16* Qs = reinterpret_cast<bf16*>(smem_bwd);
     bf16* Ks = Qs + BLK * LDS;
@@ -389,6 +393,8 @@ __global__ void __launch_bounds__(128, 4) lm_attention_bwd_single_kernel(const b
                                                                          const bf16* __restrict__ o, const bf16* __restrict__ d_o,
                                                                          const float* __restrict__ lse, bf16* __restrict__ dqkv,
                                                                          int T, int H) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t smem_bwd[];
     bf16* Qs = reinterpret_cast<bf16*>(smem_bwd);
     bf16* Ks = Qs + BLK * LDS;
@@ -548,6 +554,8 @@ __global__ void __launch_bounds__(128, 4) lm_attention_bwd_single_kernel(const b
 // ------------------------------------------------------------------------------------------ KV cache / decode
 __global__ void kv_cache_fill_kernel(const uint4* __restrict__ qkv, uint4* __restrict__ cache, int B, int T, int Tmax,
                                      int d8) {
+    pdl_trigger();
+    pdl_wait();
     // per token row: copy the 2d bf16 (k | v) that follow the d query values
     const int64_t total = static_cast<int64_t>(B) * T * 2 * d8;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -562,6 +570,11 @@ __global__ void kv_cache_fill_kernel(const uint4* __restrict__ qkv, uint4* __res
 __global__ void __launch_bounds__(128) lm_attention_decode_kernel(const bf16* __restrict__ qkv_new, bf16* __restrict__ cache,
                                                                   const int* __restrict__ valid, int valid_stride,
                                                                   bf16* __restrict__ o, int B, int H, int pos, int Tmax) {
+    pdl_trigger();
+    pdl_wait();
+    // One warp per (sample, head).  Scores: lanes over keys (each lane dots whole 128-B key rows, 8 independent 16-B
+    // loads in flight).  P.V: 4 keys per iteration, 8 lanes x 16 B per value row, partial sums folded by two shuffles
+    // -- the first version walked the values one key at a time (150 dependent iterations, 40 us per layer).
     extern __shared__ float sc[];     // [4 warps][Tmax] scores
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.x * 4 + warp;
@@ -571,8 +584,7 @@ __global__ void __launch_bounds__(128) lm_attention_decode_kernel(const bf16* __
     float* s = sc + warp * Tmax;
     const bf16* qrow = qkv_new + static_cast<int64_t>(b) * 3 * d + h * HD;
     bf16* crow = cache + static_cast<int64_t>(b) * Tmax * 2 * d;
-    // append this step's k, v (2 elements per lane each)
-    {
+    {   // append this step's k, v (2 elements per lane each)
         const uint32_t kk = *reinterpret_cast<const uint32_t*>(qrow + d + 2 * lane);
         const uint32_t vv = *reinterpret_cast<const uint32_t*>(qrow + 2 * d + 2 * lane);
         *reinterpret_cast<uint32_t*>(crow + static_cast<int64_t>(pos) * 2 * d + h * HD + 2 * lane) = kk;
@@ -595,15 +607,17 @@ __global__ void __launch_bounds__(128) lm_attention_decode_kernel(const bf16* __
         float acc = -INFINITY;
         if (valid[static_cast<int64_t>(b) * valid_stride + t]) {
             const uint4* kp = reinterpret_cast<const uint4*>(crow + static_cast<int64_t>(t) * 2 * d + h * HD);
+            uint4 u[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u[c] = kp[c];
             acc = 0.f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const uint4 u = kp[c];
                 float2 f;
-                f = unpack_bf16x2(u.x); acc += q[c * 8 + 0] * f.x + q[c * 8 + 1] * f.y;
-                f = unpack_bf16x2(u.y); acc += q[c * 8 + 2] * f.x + q[c * 8 + 3] * f.y;
-                f = unpack_bf16x2(u.z); acc += q[c * 8 + 4] * f.x + q[c * 8 + 5] * f.y;
-                f = unpack_bf16x2(u.w); acc += q[c * 8 + 6] * f.x + q[c * 8 + 7] * f.y;
+                f = unpack_bf16x2(u[c].x); acc += q[c * 8 + 0] * f.x + q[c * 8 + 1] * f.y;
+                f = unpack_bf16x2(u[c].y); acc += q[c * 8 + 2] * f.x + q[c * 8 + 3] * f.y;
+                f = unpack_bf16x2(u[c].z); acc += q[c * 8 + 4] * f.x + q[c * 8 + 5] * f.y;
+                f = unpack_bf16x2(u[c].w); acc += q[c * 8 + 6] * f.x + q[c * 8 + 7] * f.y;
             }
             acc *= 0.125f;
         }
@@ -621,17 +635,35 @@ __global__ void __launch_bounds__(128) lm_attention_decode_kernel(const bf16* __
     sum = warp_sum(sum);
     __syncwarp();
     const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-    float a0 = 0.f, a1 = 0.f;
-    const bf16* vbase = crow + d + h * HD + 2 * lane;
-    for (int t = 0; t < n; ++t) {
+    // P.V: lane = (key slot ks = lane / 8, column group cg = lane % 8 -> columns 8 cg .. 8 cg + 7)
+    const int ks = lane >> 3, cg = lane & 7;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const bf16* vbase = crow + d + h * HD + cg * 8;
+#pragma unroll 4
+    for (int t = ks; t < n; t += 4) {
         const float p = s[t];
-        if (p != 0.f) {
-            const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vbase + static_cast<int64_t>(t) * 2 * d));
-            a0 += p * f.x;
-            a1 += p * f.y;
-        }
+        const uint4 u = *reinterpret_cast<const uint4*>(vbase + static_cast<int64_t>(t) * 2 * d);
+        float2 f;
+        f = unpack_bf16x2(u.x); acc[0] += p * f.x; acc[1] += p * f.y;
+        f = unpack_bf16x2(u.y); acc[2] += p * f.x; acc[3] += p * f.y;
+        f = unpack_bf16x2(u.z); acc[4] += p * f.x; acc[5] += p * f.y;
+        f = unpack_bf16x2(u.w); acc[6] += p * f.x; acc[7] += p * f.y;
     }
-    *reinterpret_cast<uint32_t*>(o + static_cast<int64_t>(b) * d + h * HD + 2 * lane) = pack_bf16x2(a0 * inv, a1 * inv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    if (ks == 0) {
+        uint4 out;
+        out.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+        out.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+        out.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
+        out.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+        *reinterpret_cast<uint4*>(o + static_cast<int64_t>(b) * d + h * HD + cg * 8) = out;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ mapper attention, tensor-core path
@@ -690,6 +722,8 @@ __device__ __forceinline__ void scores32(float (&acc)[4][4], const bf16* As, con
 
 template <int HDIM>
 __global__ void __launch_bounds__(64) mapper_attention_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int S, int H) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int LD = HDIM + 8;
     __shared__ __align__(16) bf16 Qs[32 * LD];
     __shared__ __align__(16) bf16 Ks[32 * LD];
@@ -770,6 +804,8 @@ __global__ void __launch_bounds__(64) mapper_attention_fwd_mma_kernel(const bf16
 template <int HDIM>
 __global__ void __launch_bounds__(64) mapper_attention_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
                                                                       bf16* __restrict__ dqkv, int S, int H) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int LD = HDIM + 8, LP = 40;
     extern __shared__ __align__(16) uint8_t smem_map[];
     bf16* Qs = reinterpret_cast<bf16*>(smem_map);
@@ -887,6 +923,8 @@ __global__ void __launch_bounds__(64) mapper_attention_bwd_mma_kernel(const bf16
 // smem (fp32): q, k, v [S][hd+1]  (+ do for backward), p [S][S+1] (+ dp)
 __global__ void __launch_bounds__(128) mapper_attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int S,
                                                                    int H, int hd) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];
     const int ldh = hd + 1, ldp = S + 1;
     float* q = sm;
@@ -939,6 +977,8 @@ __global__ void __launch_bounds__(128) mapper_attention_fwd_kernel(const bf16* _
 
 __global__ void __launch_bounds__(128) mapper_attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
                                                                    bf16* __restrict__ dqkv, int S, int H, int hd) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];
     const int ldh = hd + 1, ldp = S + 1;
     float* q = sm;
@@ -1016,7 +1056,7 @@ __global__ void __launch_bounds__(128) mapper_attention_bwd_kernel(const bf16* _
 // ============================================================================================ launchers
 void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, int B, int T, int H, cudaStream_t s) {
     dim3 grid(ceil_div(T, BLK), H, B);
-    lm_attention_fwd_kernel<<<grid, 128, 0, s>>>(qkv, valid, o, lse, T, H);
+    launch_kernel(lm_attention_fwd_kernel, dim3(grid), dim3(128), 0, s, qkv, valid, o, lse, T, H);
     KERNEL_CHECK();
     count_launch();
 }
@@ -1037,12 +1077,12 @@ void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf
             CUDA_CHECK(cudaFuncSetAttribute(lm_attention_bwd_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured1 = true;
         }
-        lm_attention_bwd_single_kernel<<<grid, 128, smem, s>>>(qkv, valid, o, d_o, lse, dqkv, T, H);
+        launch_kernel(lm_attention_bwd_single_kernel, dim3(grid), dim3(128), smem, s, qkv, valid, o, d_o, lse, dqkv, T, H);
         KERNEL_CHECK();
         count_launch();
         return;
     }
-    lm_attention_bwd_kernel<<<grid, 128, smem, s>>>(qkv, valid, o, d_o, lse, dqkv, dq_scratch, T, H);
+    launch_kernel(lm_attention_bwd_kernel, dim3(grid), dim3(128), smem, s, qkv, valid, o, d_o, lse, dqkv, dq_scratch, T, H);
     KERNEL_CHECK();
     count_launch();
 }
@@ -1051,7 +1091,7 @@ void kv_cache_fill(const bf16* qkv, bf16* cache, int B, int T, int Tmax, int d, 
     EAVQA_CHECK(d % 8 == 0, "kv cache width");
     const int64_t total = static_cast<int64_t>(B) * T * 2 * (d / 8);
     const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 16));
-    kv_cache_fill_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(qkv), reinterpret_cast<uint4*>(cache), B, T,
+    launch_kernel(kv_cache_fill_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const uint4*>(qkv), reinterpret_cast<uint4*>(cache), B, T,
                                               Tmax, d / 8);
     KERNEL_CHECK();
     count_launch();
@@ -1062,7 +1102,7 @@ void lm_attention_decode(const bf16* qkv_new, bf16* cache, const int* valid, int
     const int smem = 4 * Tmax * sizeof(float);
     EAVQA_CHECK(smem <= 48 * 1024, "decode attention: sequence too long for the score buffer");
     EAVQA_CHECK(pos < Tmax, "decode position beyond the KV cache");
-    lm_attention_decode_kernel<<<ceil_div(B * H, 4), 128, smem, s>>>(qkv_new, cache, valid, valid_stride, o, B, H, pos, Tmax);
+    launch_kernel(lm_attention_decode_kernel, dim3(ceil_div(B * H, 4)), dim3(128), smem, s, qkv_new, cache, valid, valid_stride, o, B, H, pos, Tmax);
     KERNEL_CHECK();
     count_launch();
 }
@@ -1075,18 +1115,18 @@ static void launch_mapper_bwd_mma(const bf16* qkv, const bf16* d_o, bf16* dqkv, 
         CUDA_CHECK(cudaFuncSetAttribute(mapper_attention_bwd_mma_kernel<HDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    mapper_attention_bwd_mma_kernel<HDIM><<<dim3(H, B), 64, smem, s>>>(qkv, d_o, dqkv, S, H);
+    launch_kernel(mapper_attention_bwd_mma_kernel<HDIM>, dim3(dim3(H, B)), dim3(64), smem, s, qkv, d_o, dqkv, S, H);
 }
 
 void mapper_attention_fwd(const bf16* qkv, bf16* o, int B, int S, int H, int hd, cudaStream_t s) {
     if (S <= 32 && (hd == 16 || hd == 32 || hd == 64 || hd == 96 || hd == 128)) {
         dim3 grid(H, B);
         switch (hd) {
-            case 16: mapper_attention_fwd_mma_kernel<16><<<grid, 64, 0, s>>>(qkv, o, S, H); break;
-            case 32: mapper_attention_fwd_mma_kernel<32><<<grid, 64, 0, s>>>(qkv, o, S, H); break;
-            case 64: mapper_attention_fwd_mma_kernel<64><<<grid, 64, 0, s>>>(qkv, o, S, H); break;
-            case 96: mapper_attention_fwd_mma_kernel<96><<<grid, 64, 0, s>>>(qkv, o, S, H); break;
-            default: mapper_attention_fwd_mma_kernel<128><<<grid, 64, 0, s>>>(qkv, o, S, H); break;
+            case 16: launch_kernel(mapper_attention_fwd_mma_kernel<16>, dim3(grid), dim3(64), 0, s, qkv, o, S, H); break;
+            case 32: launch_kernel(mapper_attention_fwd_mma_kernel<32>, dim3(grid), dim3(64), 0, s, qkv, o, S, H); break;
+            case 64: launch_kernel(mapper_attention_fwd_mma_kernel<64>, dim3(grid), dim3(64), 0, s, qkv, o, S, H); break;
+            case 96: launch_kernel(mapper_attention_fwd_mma_kernel<96>, dim3(grid), dim3(64), 0, s, qkv, o, S, H); break;
+            default: launch_kernel(mapper_attention_fwd_mma_kernel<128>, dim3(grid), dim3(64), 0, s, qkv, o, S, H); break;
         }
         KERNEL_CHECK();
         count_launch();
@@ -1100,7 +1140,7 @@ void mapper_attention_fwd(const bf16* qkv, bf16* o, int B, int S, int H, int hd,
         configured = smem;
     }
     dim3 grid(H, B);
-    mapper_attention_fwd_kernel<<<grid, 128, smem, s>>>(qkv, o, S, H, hd);
+    launch_kernel(mapper_attention_fwd_kernel, dim3(grid), dim3(128), smem, s, qkv, o, S, H, hd);
     KERNEL_CHECK();
     count_launch();
 }
@@ -1126,7 +1166,7 @@ void mapper_attention_bwd(const bf16* qkv, const bf16* d_o, bf16* dqkv, int B, i
         configured = smem;
     }
     dim3 grid(H, B);
-    mapper_attention_bwd_kernel<<<grid, 128, smem, s>>>(qkv, d_o, dqkv, S, H, hd);
+    launch_kernel(mapper_attention_bwd_kernel, dim3(grid), dim3(128), smem, s, qkv, d_o, dqkv, S, H, hd);
     KERNEL_CHECK();
     count_launch();
 }

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256) convert_transpose_kernel(const T* __restr
                                                                 bf16* __restrict__ dst, int ld_dst,
                                                                 bf16* __restrict__ dst_t, int ld_t,
                                                                 float* __restrict__ colsum) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[32][33];
     __shared__ float cs[8][32];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -61,6 +63,8 @@ __global__ void __launch_bounds__(256) convert_transpose_kernel(const T* __restr
 
 __global__ void broadcast_rows_kernel(const float4* __restrict__ src, int n4, float4* __restrict__ dst,
                                       int64_t batch_stride4, int B) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = static_cast<int64_t>(B) * n4;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -71,6 +75,8 @@ __global__ void broadcast_rows_kernel(const float4* __restrict__ src, int n4, fl
 
 __global__ void sum_over_batch_kernel(const float* __restrict__ src, int64_t batch_stride, int B, int n,
                                       float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     float s = 0.f;
@@ -86,6 +92,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ beta, bf16* __restrict__ y,
                                                             int ld_y, float* __restrict__ mean_out,
                                                             float* __restrict__ rstd_out, int M, int d, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
     if (m >= M) return;
@@ -143,6 +151,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
                                                             int ld_dx, int accumulate, bf16* __restrict__ dx_bf16,
                                                             int ld_dxb, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int M, int d) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float red[];   // PARAM_GRADS: [2][d] block-level dgamma / dbeta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
@@ -243,6 +253,8 @@ __global__ void __launch_bounds__(256, (MAXV <= 6) ? 4 : (MAXV <= 10) ? 3 : 2) l
                                                                     const float* __restrict__ rstd_in, float* __restrict__ dx,
                                                                     int ld_dx, int accumulate, bf16* __restrict__ dx_bf16,
                                                                     int ld_dxb, int M, int d) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
     if (m >= M) return;
@@ -309,6 +321,8 @@ __global__ void __launch_bounds__(256) ln_param_grad_kernel(const bf16* __restri
                                                             int ld_x, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int M, int d) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sg[8][64], sb[8][64];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int c = blockIdx.x * 64 + 2 * tx;
@@ -346,6 +360,8 @@ __global__ void __launch_bounds__(256) ln_param_grad_kernel(const bf16* __restri
 // ------------------------------------------------------------------------------------------ embedding / splice
 __global__ void prepend_plan_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ mask, int B, int Tt,
                                     int P, int* __restrict__ plan, int* __restrict__ valid) {
+    pdl_trigger();
+    pdl_wait();
     const int T = P + Tt;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * T) return;
@@ -364,6 +380,8 @@ __global__ void prepend_plan_kernel(const int64_t* __restrict__ tokens, const in
 __global__ void splice_plan_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ mask, int B, int Tt,
                                    int P, int n_img, int64_t sent_lo, int64_t sent_hi, int* __restrict__ plan,
                                    int* __restrict__ valid, int* __restrict__ err_flag) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     const int b = warp;
@@ -403,6 +421,8 @@ __global__ void __launch_bounds__(256) embed_rows_kernel(const int* __restrict__
                                                          const float* __restrict__ prefix, int64_t prefix_batch_stride,
                                                          int prefix_row_stride, const float* __restrict__ wpe,
                                                          float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= rows) return;
@@ -430,6 +450,8 @@ __global__ void __launch_bounds__(256) embed_rows_kernel(const int* __restrict__
 // ------------------------------------------------------------------------------------------ cross-entropy
 __global__ void ce_plan_kernel(const int64_t* __restrict__ labels, int B, int Tt, int T, int P, int vocab,
                                int* __restrict__ row_index, int* __restrict__ label, int* __restrict__ n_valid) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     bool ok = false;
     if (r < B * Tt) {
@@ -447,6 +469,8 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(const float2* __restri
                                                           const float* __restrict__ target,
                                                           const int* __restrict__ label, float* __restrict__ lse,
                                                           float* __restrict__ loss_sum, int M) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float block_loss[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + warp;
@@ -481,12 +505,16 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(const float2* __restri
 }
 
 __global__ void ce_loss_kernel(const float* loss_sum, const int* n_valid, float* loss_out) {
+    pdl_trigger();
+    pdl_wait();
     *loss_out = *loss_sum / static_cast<float>(*n_valid);    // 0/0 = NaN, like the mean over no targets
 }
 
 __global__ void __launch_bounds__(256) ce_dlogits_kernel(bf16* __restrict__ z, int ld, int vocab, int n_cols,
                                                          const float* __restrict__ lse, const int* __restrict__ label,
                                                          const int* __restrict__ n_valid) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x;
     const int lab = label[r];
     uint4* zp = reinterpret_cast<uint4*>(z + static_cast<size_t>(r) * ld);
@@ -535,6 +563,8 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
                                                           const float* __restrict__ wpe_row, int d,
                                                           float* __restrict__ x_next, int* __restrict__ valid_next,
                                                           int valid_stride) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_val[8];
     __shared__ int s_idx[8];
     __shared__ int s_next;
@@ -542,12 +572,28 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
     const float* lp = logits + static_cast<size_t>(b) * ld;
     float best = -INFINITY;
     int best_i = 0x7fffffff;
-    for (int v = threadIdx.x; v < vocab; v += blockDim.x) {
-        const float x = lp[v];
-        if (x > best) {          // strided scan visits increasing v: first maximum wins within a thread
-            best = x;
-            best_i = v;
+    // rows are 16-byte aligned (ld % 4 == 0): float4 loads, 4 of them in flight per thread; ties keep the lowest index
+    const float4* lp4 = reinterpret_cast<const float4*>(lp);
+    const int n4 = vocab >> 2;
+    for (int v0 = threadIdx.x; v0 < n4; v0 += 4 * blockDim.x) {
+        float4 x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = v0 + k * blockDim.x;
+            x[k] = v < n4 ? lp4[v] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = (v0 + k * blockDim.x) * 4;
+            if (x[k].x > best) { best = x[k].x; best_i = v; }
+            if (x[k].y > best) { best = x[k].y; best_i = v + 1; }
+            if (x[k].z > best) { best = x[k].z; best_i = v + 2; }
+            if (x[k].w > best) { best = x[k].w; best_i = v + 3; }
+        }
+    }
+    for (int v = (n4 << 2) + threadIdx.x; v < vocab; v += blockDim.x) {
+        const float x = lp[v];
+        if (x > best || (x == best && v < best_i)) { best = x; best_i = v; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -599,6 +645,8 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
 __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                                                     float4* __restrict__ v, int64_t n4, float lr, float beta1, float beta2,
                                                     float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
@@ -628,7 +676,7 @@ void adamw_step(float* params, const float* grads, float* m, float* v, int64_t n
     const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
     const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
     const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(n / 4, 256), static_cast<int64_t>(num_sms()) * 8));
-    adamw_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads),
+    launch_kernel(adamw_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads),
                                       reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n / 4, lr, beta1, beta2, eps,
                                       weight_decay, bc1, sqrtf(bc2), grad_scale);
     KERNEL_CHECK();
@@ -638,14 +686,14 @@ void adamw_step(float* params, const float* grads, float* m, float* v, int64_t n
 void convert_transpose_f32(const float* src, int ld_src, int R, int C, bf16* dst, int ld_dst, bf16* dst_t, int ld_t,
                            float* colsum, cudaStream_t s) {
     dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);
-    convert_transpose_kernel<float><<<grid, block, 0, s>>>(src, ld_src, R, C, dst, ld_dst, dst_t, ld_t, colsum);
+    launch_kernel(convert_transpose_kernel<float>, dim3(grid), dim3(block), 0, s, src, ld_src, R, C, dst, ld_dst, dst_t, ld_t, colsum);
     KERNEL_CHECK();
     count_launch();
 }
 void convert_transpose_bf16(const bf16* src, int ld_src, int R, int C, bf16* dst_t, int ld_t, float* colsum,
                             cudaStream_t s) {
     dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);
-    convert_transpose_kernel<bf16><<<grid, block, 0, s>>>(src, ld_src, R, C, nullptr, 0, dst_t, ld_t, colsum);
+    launch_kernel(convert_transpose_kernel<bf16>, dim3(grid), dim3(block), 0, s, src, ld_src, R, C, nullptr, 0, dst_t, ld_t, colsum);
     KERNEL_CHECK();
     count_launch();
 }
@@ -654,13 +702,13 @@ void broadcast_rows_f32(const float* src, int rows, int d, float* dst, int64_t b
     const int n4 = rows * d / 4;
     const int64_t total = static_cast<int64_t>(B) * n4;
     const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 8));
-    broadcast_rows_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(src), n4, reinterpret_cast<float4*>(dst),
+    launch_kernel(broadcast_rows_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float4*>(src), n4, reinterpret_cast<float4*>(dst),
                                                batch_stride / 4, B);
     KERNEL_CHECK();
     count_launch();
 }
 void sum_over_batch_f32(const float* src, int64_t batch_stride, int B, int n, float* out, cudaStream_t s) {
-    sum_over_batch_kernel<<<ceil_div(n, 256), 256, 0, s>>>(src, batch_stride, B, n, out);
+    launch_kernel(sum_over_batch_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, s, src, batch_stride, B, n, out);
     KERNEL_CHECK();
     count_launch();
 }
@@ -671,7 +719,7 @@ void layernorm_fwd(const float* x, int ld_x, const int* row_index, const float* 
     EAVQA_CHECK(d % 4 == 0 && d <= 2048 && ld_x % 4 == 0 && ld_y % 4 == 0, "layernorm width must be a multiple of 4 and <= 2048");
     const int need = ceil_div(d / 4, 32);
     const int grid = ceil_div(M, 8);
-#define EAVQA_LN_FWD(V) layernorm_fwd_kernel<V><<<grid, 256, 0, s>>>(x, ld_x, row_index, gamma, beta, y, ld_y, mean, rstd, M, d, eps)
+#define EAVQA_LN_FWD(V) launch_kernel(layernorm_fwd_kernel<V>, dim3(grid), dim3(256), 0, s, x, ld_x, row_index, gamma, beta, y, ld_y, mean, rstd, M, d, eps)
     if (need <= 2) EAVQA_LN_FWD(2);
     else if (need <= 4) EAVQA_LN_FWD(4);
     else if (need <= 6) EAVQA_LN_FWD(6);
@@ -691,7 +739,7 @@ static void launch_ln_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, c
     if (dgamma != nullptr && row_index != nullptr) {
         // gathered rows + parameter gradients: not on the step's path; keep the fused (register-heavy) variant
         const int grid = std::min(ceil_div(M, 8), 2 * num_sms());
-        layernorm_bwd_kernel<MAXV, true><<<grid, 256, 2 * d * sizeof(float), s>>>(
+        launch_kernel(layernorm_bwd_kernel<MAXV, true>, dim3(grid), dim3(256), 2 * d * sizeof(float), s, 
             dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx, accumulate, dx_bf16, ld_dxb, dgamma, dbeta, M, d);
         KERNEL_CHECK();
         count_launch();
@@ -701,7 +749,7 @@ static void launch_ln_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, c
     // re-reads dy and x (L2-resident) in a second, occupancy-friendly kernel instead
     if (dgamma != nullptr) layernorm_param_grads(dy, ld_dy, x, ld_x, mean, rstd, dgamma, dbeta, M, d, s);
     const int grid = ceil_div(M, 8);
-    layernorm_bwd_lean_kernel<MAXV><<<grid, 256, 0, s>>>(dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx,
+    launch_kernel(layernorm_bwd_lean_kernel<MAXV>, dim3(grid), dim3(256), 0, s, dy, ld_dy, x, ld_x, row_index, gamma, mean, rstd, dx, ld_dx,
                                                          accumulate, dx_bf16, ld_dxb, M, d);
     KERNEL_CHECK();
     count_launch();
@@ -729,14 +777,14 @@ void layernorm_param_grads(const bf16* dy, int ld_dy, const float* x, int ld_x, 
                            float* dgamma, float* dbeta, int M, int d, cudaStream_t s) {
     EAVQA_CHECK(d % 2 == 0 && ld_dy % 2 == 0 && ld_x % 2 == 0, "layernorm_param_grads alignment");
     dim3 grid(ceil_div(d, 64), ceil_div(M, 256)), block(32, 8);
-    ln_param_grad_kernel<<<grid, block, 0, s>>>(dy, ld_dy, x, ld_x, mean, rstd, dgamma, dbeta, M, d);
+    launch_kernel(ln_param_grad_kernel, dim3(grid), dim3(block), 0, s, dy, ld_dy, x, ld_x, mean, rstd, dgamma, dbeta, M, d);
     KERNEL_CHECK();
     count_launch();
 }
 
 void prepend_plan(const int64_t* tokens, const int64_t* mask, int B, int Tt, int P, int* plan, int* valid, cudaStream_t s) {
     const int n = B * (P + Tt);
-    prepend_plan_kernel<<<ceil_div(n, 256), 256, 0, s>>>(tokens, mask, B, Tt, P, plan, valid);
+    launch_kernel(prepend_plan_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, s, tokens, mask, B, Tt, P, plan, valid);
     KERNEL_CHECK();
     count_launch();
 }
@@ -745,7 +793,7 @@ void splice_plan(const int64_t* tokens, const int64_t* mask, int B, int Tt, int 
     const int T_out = Tt + (P - 1) * n_img;
     fill_zero(plan, sizeof(int) * static_cast<size_t>(B) * T_out, s);
     fill_zero(valid, sizeof(int) * static_cast<size_t>(B) * T_out, s);
-    splice_plan_kernel<<<ceil_div(B * 32, 128), 128, 0, s>>>(tokens, mask, B, Tt, P, n_img, sent_lo, sent_hi, plan, valid, err_flag);
+    launch_kernel(splice_plan_kernel, dim3(ceil_div(B * 32, 128)), dim3(128), 0, s, tokens, mask, B, Tt, P, n_img, sent_lo, sent_hi, plan, valid, err_flag);
     KERNEL_CHECK();
     count_launch();
 }
@@ -753,7 +801,7 @@ void embed_rows(const int* plan, int B, int T, int d, const float* wte, int voca
                 int64_t prefix_batch_stride, int prefix_row_stride, const float* wpe, float* out, cudaStream_t s) {
     EAVQA_CHECK(d % 4 == 0 && prefix_batch_stride % 4 == 0 && prefix_row_stride % 4 == 0, "embed alignment");
     const int rows = B * T;
-    embed_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(plan, rows, T, d, wte, vocab, prefix, prefix_batch_stride,
+    launch_kernel(embed_rows_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, s, plan, rows, T, d, wte, vocab, prefix, prefix_batch_stride,
                                                         prefix_row_stride, wpe, out);
     KERNEL_CHECK();
     count_launch();
@@ -762,26 +810,26 @@ void embed_rows(const int* plan, int B, int T, int d, const float* wte, int voca
 void ce_plan(const int64_t* labels, int B, int Tt, int T, int P, int vocab, int* row_index, int* label, int* n_valid,
              cudaStream_t s) {
     fill_zero(n_valid, sizeof(int), s);
-    ce_plan_kernel<<<ceil_div(B * Tt, 256), 256, 0, s>>>(labels, B, Tt, T, P, vocab, row_index, label, n_valid);
+    launch_kernel(ce_plan_kernel, dim3(ceil_div(B * Tt, 256)), dim3(256), 0, s, labels, B, Tt, T, P, vocab, row_index, label, n_valid);
     KERNEL_CHECK();
     count_launch();
 }
 void ce_finalize(const float2* partial, int tiles, const float* target, const int* label, float* lse, float* loss_sum,
                  int M, cudaStream_t s) {
     fill_zero(loss_sum, sizeof(float), s);
-    ce_finalize_kernel<<<ceil_div(M, 8), 256, 0, s>>>(partial, tiles, target, label, lse, loss_sum, M);
+    launch_kernel(ce_finalize_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, s, partial, tiles, target, label, lse, loss_sum, M);
     KERNEL_CHECK();
     count_launch();
 }
 void ce_loss(const float* loss_sum, const int* n_valid, float* loss_out, cudaStream_t s) {
-    ce_loss_kernel<<<1, 1, 0, s>>>(loss_sum, n_valid, loss_out);
+    launch_kernel(ce_loss_kernel, dim3(1), dim3(1), 0, s, loss_sum, n_valid, loss_out);
     KERNEL_CHECK();
     count_launch();
 }
 void ce_dlogits(bf16* z, int ld, int M, int vocab, int n_cols, const float* lse, const int* label, const int* n_valid,
                 cudaStream_t s) {
     EAVQA_CHECK(ld % 8 == 0 && n_cols % 8 == 0 && n_cols <= ld, "ce_dlogits alignment");
-    ce_dlogits_kernel<<<M, 256, 0, s>>>(z, ld, vocab, n_cols, lse, label, n_valid);
+    launch_kernel(ce_dlogits_kernel, dim3(M), dim3(256), 0, s, z, ld, vocab, n_cols, lse, label, n_valid);
     KERNEL_CHECK();
     count_launch();
 }
@@ -790,7 +838,7 @@ void greedy_step(const float* logits, int ld, int B, int vocab, int step, int ma
                  int64_t eos_id, int* unfinished, int64_t* tokens_out, int* n_unfinished, float* top_logit,
                  const float* wte, const float* wpe_row, int d, float* x_next, int* valid_next, int valid_stride,
                  cudaStream_t s) {
-    greedy_step_kernel<<<B, 256, 0, s>>>(logits, ld, vocab, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out,
+    launch_kernel(greedy_step_kernel, dim3(B), dim3(256), 0, s, logits, ld, vocab, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out,
                                          n_unfinished, top_logit, wte, wpe_row, d, x_next, valid_next, valid_stride);
     KERNEL_CHECK();
     count_launch();

@@ -57,6 +57,8 @@ GemmEpilogue ep_f32(float* out, int ldo, const float* bias = nullptr, const floa
 int pad8(int n) { return (n + 7) & ~7; }
 
 __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x)
         dst[i] = __bfloat162float(src[i]);
@@ -65,6 +67,8 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restri
 // dx[n, s, :] = s >= cl ? dprefix[n, s - cl, :] : 0     (gradient entering the mapper's last layer)
 __global__ void scatter_prefix_grad_kernel(const float4* __restrict__ dprefix, int64_t batch_stride4, float4* __restrict__ dx,
                                            int N, int S, int cl, int d4) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = static_cast<int64_t>(N) * S * d4;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -78,10 +82,14 @@ __global__ void scatter_prefix_grad_kernel(const float4* __restrict__ dprefix, i
 }
 
 __global__ void last_row_index_kernel(int* row_index, int B, int T) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) row_index[b] = b * T + T - 1;
 }
 __global__ void fill_int_kernel(int* p, int n, int v) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
@@ -168,7 +176,7 @@ void Engine::load_lm_weight(const std::string& name, const void* dev_ptr, int dt
     const float* src = static_cast<const float*>(dev_ptr);
     if (dtype == EAVQA_BF16) {
         float* tmp = static_cast<float*>(dmalloc(sizeof(float) * numel));
-        bf16_to_f32_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(numel, 256), 4096)), 256, 0, s>>>(
+        launch_kernel(bf16_to_f32_kernel, dim3(static_cast<int>(std::min<int64_t>(ceil_div64(numel, 256), 4096))), dim3(256), 0, s, 
             static_cast<const bf16*>(dev_ptr), tmp, numel);
         KERNEL_CHECK();
         src = tmp;
@@ -409,7 +417,7 @@ void Engine::mapper_backward(const float* params, const MapperW& w, const Mapper
     if (grads == nullptr) return;         // planning pass only
     {
         const int64_t total = static_cast<int64_t>(M2) * (d / 4);
-        scatter_prefix_grad_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 8)), 256, 0, s>>>(
+        launch_kernel(scatter_prefix_grad_kernel, dim3(static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 8))), dim3(256), 0, s, 
             reinterpret_cast<const float4*>(dprefix), dprefix_batch_stride / 4, reinterpret_cast<float4*>(dx), N, S, cl, d / 4);
         KERNEL_CHECK();
         count_launch();
@@ -495,7 +503,8 @@ void Engine::train_step(int B, int Tt, const float* clip, const int64_t* tokens,
     const int d = d_, L = L_, T = P_ + Tt, M = B * T, Mh = B * Tt;
     EAVQA_CHECK(T <= cfg_.n_positions, "sequence longer than n_positions");
     const bool bwd = grads != nullptr;
-    const int head_bn = gemm_pick_block_n(Mh, Vpad_, d, 0);
+    int head_bn = 0, head_cluster = 1;
+    gemm_pick_config(Mh, Vpad_, d, 0, 0, &head_bn, &head_cluster);
     const int head_tiles = 2 * ceil_div(Vpad_, head_bn);   // one (max, sum-exp) pair per half N-tile
 
     MapperW mw;
@@ -664,7 +673,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     int* err_flag = flags + max_new;
     fill_zero(flags, sizeof(int) * (max_new + 1), s);
     fill_zero(validD, sizeof(int) * static_cast<size_t>(B) * Tmax, s);
-    fill_int_kernel<<<ceil_div(B, 256), 256, 0, s>>>(unfinished, B, 1);
+    launch_kernel(fill_int_kernel, dim3(ceil_div(B, 256)), dim3(256), 0, s, unfinished, B, 1);
     KERNEL_CHECK();
     count_launch();
 
@@ -695,7 +704,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         float* t = ha; ha = hcur; hcur = hb; hb = t;      // output becomes next input
     }
     // logits only at the LAST position of every row, pad or not (clipcap.py:420, quirk Q2)
-    last_row_index_kernel<<<ceil_div(B, 256), 256, 0, s>>>(row_index, B, T0);
+    launch_kernel(last_row_index_kernel, dim3(ceil_div(B, 256)), dim3(256), 0, s, row_index, B, T0);
     KERNEL_CHECK();
     count_launch();
     auto head_and_pick = [&](const float* hidden, const int* rows, int step) {

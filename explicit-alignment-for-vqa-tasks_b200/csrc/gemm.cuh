@@ -36,6 +36,8 @@ struct GemmEpilogue {
     const int* ce_label = nullptr;   // [M], -1 = none
     int ce_tiles = 0;
     int n_valid = 0;
+    int debug = 0;                   // EAVQA_GEMM_DEBUG (timing experiments only; results are wrong when non-zero):
+                                     // 1 = issue every other TMA store, 2 = no TMA stores, 3 = no staging and no stores
 };
 
 struct GemmArgs {
@@ -44,13 +46,15 @@ struct GemmArgs {
     int lda = 0, ldb = 0;            // row strides in elements (multiples of 8)
     int M = 0, N = 0, K = 0;
     int block_n = 0;                 // 0 = pick by wave-quantisation heuristic; else 64/128/192/256
-    int cluster = 0;                 // 0 = heuristic; 1 = single CTAs; 2 = 2x1 cluster (B multicast); 4 = 2x2 (A and B)
+    int cluster = 0;                 // 0 = heuristic; 1 = single CTAs; 8 = CTA pair (cta_group::2); 2 / 4 = multicast clusters
     GemmEpilogue ep;
 };
 
 // Number of N tiles the heuristic (or block_n) will use: callers size ce_partial with it.
 int gemm_pick_block_n(int M, int N, int K, int forced);
 int gemm_pick_cluster(int M, int N, int bn, int forced);
+// tile width + CTA mode (1 = single CTAs, 8 = CTA pair / cta_group::2) the launcher will use for this problem
+void gemm_pick_config(int M, int N, int K, int forced_bn, int forced_cluster, int* bn_out, int* cluster_out);
 void gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream);
 // kernels this translation unit launched since process start (bench.py's gpu_launches)
 int64_t gemm_launch_count();

@@ -13,6 +13,8 @@
 // the residual / activation-derivative operand is fetched the same way, one chunk ahead.  (Round-1 profile: the
 // first version stored straight from registers, one row per thread -> 32 LSU wavefronts per store instruction,
 // and K=768 GEMMs ran at 340-470 TFLOP/s; see profiles/.)
+#include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -143,6 +145,226 @@ struct TmaMaps {
     CUtensorMap a, b, out, out2, in;
 };
 
+// ---------------------------------------------------------------------------------------------
+// epilogue role (8 warps), shared by the 1-CTA and the 2-CTA (cta_group::2) kernels
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool CE, class Coords, class Release>
+__device__ __forceinline__ void epilogue_role(const TmaMaps& maps, const GemmEpilogue& ep, int M, int N, int num_n, int num_tiles,
+                                              int tile_begin, int tile_step, Coords coords, Release release_tmem,
+                                              uint32_t tmem_base, uint32_t tfull_bar, uint32_t smem_epi, uint32_t in_bar0,
+                                              int warp, int lane) {
+    using C = Cfg<BN>;
+    const int ew = warp - 2;                      // 0..7
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                     // which half of the tile's columns
+    const uint32_t bufA = smem_epi + ew * 2 * EPI_BUF;
+    const uint32_t bufB = bufA + EPI_BUF;
+    const uint32_t in_bar = in_bar0 + 8 * ew;
+    const bool has_res = ep.residual != nullptr;
+    const bool has_aux = ep.dact != DACT_NONE;
+    const bool has_in = has_res || has_aux;
+    const bool out_f32 = ep.out_fp32 != 0;
+    const uint32_t in_bytes = has_res ? 32u * 128u : 32u * 64u;
+    uint32_t in_phase = 0;
+    uint32_t out_slot = 0;                        // bf16 outputs alternate between two 2-KB halves of the buffers
+    pdl_wait();           // first global access of these warps comes next (operand prefetch, bias, labels, stores)
+
+    auto n_valid_chunks = [&](int n_idx) {
+        const int col0 = n_idx * BN + half * C::HALF;
+        const int rem = N - col0;
+        return rem <= 0 ? 0 : min(C::NCHUNK, (rem + CHUNK - 1) / CHUNK);
+    };
+    auto issue_in = [&](int tile, int c) {        // lane 0 only
+        int m_idx, n_idx;
+        coords(tile, m_idx, n_idx);
+        ptx::mbar_arrive_expect_tx(in_bar, in_bytes);
+        ptx::tma_load_2d(bufB, &maps.in, in_bar, n_idx * BN + half * C::HALF + c * CHUNK, m_idx * BM + quarter * 32);
+    };
+    auto next_tile_with_work = [&](int tile) {
+        int t = tile;
+        while (t < num_tiles) {
+            int m_idx, n_idx;
+            coords(t, m_idx, n_idx);
+            if (n_valid_chunks(n_idx) > 0) break;
+            t += tile_step;
+        }
+        return t;
+    };
+    if (has_in && lane == 0) {
+        const int t0 = next_tile_with_work(tile_begin);
+        if (t0 < num_tiles) issue_in(t0, 0);
+    }
+
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
+        int m_idx, n_idx;
+        coords(tile, m_idx, n_idx);
+        const int row0 = m_idx * BM + quarter * 32;
+        const int row = row0 + lane;
+        const bool row_ok = row < M;
+        const int col_base = n_idx * BN + half * C::HALF;
+        const int nvalid = n_valid_chunks(n_idx);
+
+        // this warp's slice of the bias vector: lane l keeps column (32k + l) of every chunk, broadcast by shuffle
+        float bias_reg[C::NCHUNK];
+#pragma unroll
+        for (int k = 0; k < C::NCHUNK; ++k) {
+            const int n = col_base + k * 32 + lane;
+            bias_reg[k] = (ep.bias != nullptr && n < N) ? __ldg(ep.bias + n) : 0.f;
+        }
+
+        ptx::mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        ptx::tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * C::HALF;
+        if (nvalid == 0) {
+            ptx::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) release_tmem(acc);
+        }
+        float ce_m = -INFINITY, ce_s = 0.f;
+        int label = -1;
+        if (CE && row_ok && ep.ce_label != nullptr) label = __ldg(ep.ce_label + row);
+
+        uint32_t r[32];
+        if (nvalid > 0) ptx::tmem_ld_32x32(taddr, r);
+#pragma unroll
+        for (int c = 0; c < C::NCHUNK; ++c) {
+            if (c >= nvalid) break;               // warp-uniform
+            const int n0 = col_base + c * CHUNK;
+            ptx::tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (c + 1 < nvalid) {
+                ptx::tmem_ld_32x32(taddr + (c + 1) * CHUNK, r);       // overlaps this chunk's math / staging
+            } else {
+                ptx::tcgen05_fence_before();                          // accumulator fully read: release the TMEM buffer
+                __syncwarp();
+                if (lane == 0) release_tmem(acc);
+            }
+            if (ep.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_reg[c], j);
+            }
+            if (CE) {
+                // running max / sum-exp over the valid vocabulary columns; the label's logit in fp32
+                float cm = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n0 + j < ep.n_valid) cm = fmaxf(cm, v[j]);
+                if (cm > -INFINITY) {
+                    const float nm = fmaxf(ce_m, cm);
+                    float a = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j < ep.n_valid) a += __expf(v[j] - nm);
+                    ce_s = ce_s * __expf(ce_m - nm) + a;
+                    ce_m = nm;
+                }
+                if (row_ok && label >= n0 && label < n0 + 32) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j == label) t = v[j];
+                    ep.ce_target[row] = t;
+                }
+            }
+            const uint32_t slot_off = out_f32 ? 0u : (out_slot & 1u) * 2048u;
+            // staging buffers of this slot must have been read out by their previous TMA store
+            if (lane == 0) {
+                if (out_f32) tma_store_wait_read<0>();
+                else tma_store_wait_read<1>();
+            }
+            __syncwarp();
+            if (ep.out2 != nullptr) {             // pre-activation, bf16 (bufB is free: no mode has out2 and an input operand)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    st_shared_v4(bufB + slot_off + swz64(lane, q), pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]),
+                                 pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]),
+                                 pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+            }
+            if (ep.act == ACT_GELU_NEW) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_new(v[j]);
+            } else if (ep.act == ACT_TANH) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+            } else if (ep.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (has_in) {
+                ptx::mbar_wait(in_bar, in_phase);
+                in_phase ^= 1;
+                if (has_res) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint4 u = ld_shared_v4(bufB + swz128(lane, q));
+                        v[q * 4 + 0] += __uint_as_float(u.x); v[q * 4 + 1] += __uint_as_float(u.y);
+                        v[q * 4 + 2] += __uint_as_float(u.z); v[q * 4 + 3] += __uint_as_float(u.w);
+                    }
+                } else {
+                    float a[32];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 u = ld_shared_v4(bufB + swz64(lane, q));
+                        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                        a[q * 8 + 0] = f0.x; a[q * 8 + 1] = f0.y; a[q * 8 + 2] = f1.x; a[q * 8 + 3] = f1.y;
+                        a[q * 8 + 4] = f2.x; a[q * 8 + 5] = f2.y; a[q * 8 + 6] = f3.x; a[q * 8 + 7] = f3.y;
+                    }
+                    if (ep.dact == DACT_GELU_NEW) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= gelu_new_grad(a[j]);
+                    } else if (ep.dact == DACT_TANH) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= (1.0f - a[j] * a[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = (a[j] > 0.f) ? v[j] : 0.f;
+                    }
+                }
+                __syncwarp();                     // every lane has consumed bufB: fetch the next chunk's operand
+                if (lane == 0) {
+                    if (c + 1 < nvalid) {
+                        issue_in(tile, c + 1);
+                    } else {
+                        const int tn = next_tile_with_work(tile + tile_step);
+                        if (tn < num_tiles) issue_in(tn, 0);
+                    }
+                }
+            }
+            if (ep.out != nullptr && ep.debug != 3) {
+                if (out_f32) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        st_shared_v4(bufA + swz128(lane, q), __float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
+                                     __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        st_shared_v4(bufA + slot_off + swz64(lane, q), pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]),
+                                     pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]),
+                                     pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+                }
+            }
+            ptx::fence_proxy_async_smem();        // generic-proxy writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0 && !(ep.debug == 2 || ep.debug == 3 || (ep.debug == 1 && (out_slot & 1)))) {
+                if (ep.out != nullptr) tma_store_2d(&maps.out, bufA + slot_off, n0, row0);
+                if (ep.out2 != nullptr) tma_store_2d(&maps.out2, bufB + slot_off, n0, row0);
+                tma_store_commit();
+            }
+            ++out_slot;
+        }
+        if (CE && row_ok && n_idx < num_n)
+            ep.ce_partial[static_cast<size_t>(row) * ep.ce_tiles + n_idx * 2 + half] = make_float2(ce_m, ce_s);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_read<0>();      // staging smem must outlive the last bulk stores
+}
+
 // CM x CN thread-block cluster: the CM CTAs of a cluster column share one B tile and the CN CTAs of a cluster row
 // share one A tile; each CTA fetches 1/CM of B (1/CN of A) and TMA-multicasts it to its peers, so every operand
 // byte crosses the L2 -> SM fabric once per cluster instead of once per CTA.  (Round-1 measurement: with single
@@ -182,6 +404,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();        // the next kernel may be scheduled; it blocks in its own pdl_wait() until this grid completes
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&maps.a);
@@ -229,6 +452,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
     if (warp == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
+            pdl_wait();       // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
@@ -285,214 +509,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
         }
     } else {
         // ===================== epilogue warps =====================
-        const int ew = warp - 2;                      // 0..7
-        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                     // which half of the tile's columns
-        const uint32_t bufA = smem_epi + ew * 2 * EPI_BUF;
-        const uint32_t bufB = bufA + EPI_BUF;
-        const uint32_t in_bar = in_bar0 + 8 * ew;
-        const bool has_res = ep.residual != nullptr;
-        const bool has_aux = ep.dact != DACT_NONE;
-        const bool has_in = has_res || has_aux;
-        const bool out_f32 = ep.out_fp32 != 0;
-        const uint32_t in_bytes = has_res ? 32u * 128u : 32u * 64u;
-        uint32_t in_phase = 0;
-        uint32_t out_slot = 0;                        // bf16 outputs alternate between two 2-KB halves of the buffers
-
-        auto n_valid_chunks = [&](int n_idx) {
-            const int col0 = n_idx * BN + half * C::HALF;
-            const int rem = N - col0;
-            return rem <= 0 ? 0 : min(C::NCHUNK, (rem + CHUNK - 1) / CHUNK);
-        };
-        auto issue_in = [&](int tile, int c) {        // lane 0 only
-            int m_idx, n_idx;
-            coords(tile, m_idx, n_idx);
-            ptx::mbar_arrive_expect_tx(in_bar, in_bytes);
-            ptx::tma_load_2d(bufB, &maps.in, in_bar, n_idx * BN + half * C::HALF + c * CHUNK, m_idx * BM + quarter * 32);
-        };
-        auto next_tile_with_work = [&](int tile) {
-            int t = tile;
-            while (t < num_tiles) {
-                int m_idx, n_idx;
-                coords(t, m_idx, n_idx);
-                if (n_valid_chunks(n_idx) > 0) break;
-                t += tile_step;
-            }
-            return t;
-        };
-        if (has_in && lane == 0) {
-            const int t0 = next_tile_with_work(tile_begin);
-            if (t0 < num_tiles) issue_in(t0, 0);
-        }
-
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
-            int m_idx, n_idx;
-            coords(tile, m_idx, n_idx);
-            const int row0 = m_idx * BM + quarter * 32;
-            const int row = row0 + lane;
-            const bool row_ok = row < M;
-            const int col_base = n_idx * BN + half * C::HALF;
-            const int nvalid = n_valid_chunks(n_idx);
-
-            // this warp's slice of the bias vector: lane l keeps column (32k + l) of every chunk, broadcast by shuffle
-            float bias_reg[C::NCHUNK];
-#pragma unroll
-            for (int k = 0; k < C::NCHUNK; ++k) {
-                const int n = col_base + k * 32 + lane;
-                bias_reg[k] = (ep.bias != nullptr && n < N) ? __ldg(ep.bias + n) : 0.f;
-            }
-
-            ptx::mbar_wait(tfull_bar + 8 * acc, acc_phase);
-            ptx::tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * C::HALF;
-            if (nvalid == 0) {
-                ptx::tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * acc);
-            }
-            float ce_m = -INFINITY, ce_s = 0.f;
-            int label = -1;
-            if (CE && row_ok && ep.ce_label != nullptr) label = __ldg(ep.ce_label + row);
-
-            uint32_t r[32];
-            if (nvalid > 0) ptx::tmem_ld_32x32(taddr, r);
-#pragma unroll
-            for (int c = 0; c < C::NCHUNK; ++c) {
-                if (c >= nvalid) break;               // warp-uniform
-                const int n0 = col_base + c * CHUNK;
-                ptx::tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (c + 1 < nvalid) {
-                    ptx::tmem_ld_32x32(taddr + (c + 1) * CHUNK, r);       // overlaps this chunk's math / staging
-                } else {
-                    ptx::tcgen05_fence_before();                          // accumulator fully read: release the TMEM buffer
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * acc);
-                }
-                if (ep.bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_reg[c], j);
-                }
-                if (CE) {
-                    // running max / sum-exp over the valid vocabulary columns; the label's logit in fp32
-                    float cm = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + j < ep.n_valid) cm = fmaxf(cm, v[j]);
-                    if (cm > -INFINITY) {
-                        const float nm = fmaxf(ce_m, cm);
-                        float a = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + j < ep.n_valid) a += __expf(v[j] - nm);
-                        ce_s = ce_s * __expf(ce_m - nm) + a;
-                        ce_m = nm;
-                    }
-                    if (row_ok && label >= n0 && label < n0 + 32) {
-                        float t = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + j == label) t = v[j];
-                        ep.ce_target[row] = t;
-                    }
-                }
-                const uint32_t slot_off = out_f32 ? 0u : (out_slot & 1u) * 2048u;
-                // staging buffers of this slot must have been read out by their previous TMA store
-                if (lane == 0) {
-                    if (out_f32) tma_store_wait_read<0>();
-                    else tma_store_wait_read<1>();
-                }
-                __syncwarp();
-                if (ep.out2 != nullptr) {             // pre-activation, bf16 (bufB is free: no mode has out2 and an input operand)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        st_shared_v4(bufB + slot_off + swz64(lane, q), pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]),
-                                     pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]),
-                                     pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
-                }
-                if (ep.act == ACT_GELU_NEW) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_new(v[j]);
-                } else if (ep.act == ACT_TANH) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
-                } else if (ep.act == ACT_RELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                if (has_in) {
-                    ptx::mbar_wait(in_bar, in_phase);
-                    in_phase ^= 1;
-                    if (has_res) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const uint4 u = ld_shared_v4(bufB + swz128(lane, q));
-                            v[q * 4 + 0] += __uint_as_float(u.x); v[q * 4 + 1] += __uint_as_float(u.y);
-                            v[q * 4 + 2] += __uint_as_float(u.z); v[q * 4 + 3] += __uint_as_float(u.w);
-                        }
-                    } else {
-                        float a[32];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 u = ld_shared_v4(bufB + swz64(lane, q));
-                            const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-                            a[q * 8 + 0] = f0.x; a[q * 8 + 1] = f0.y; a[q * 8 + 2] = f1.x; a[q * 8 + 3] = f1.y;
-                            a[q * 8 + 4] = f2.x; a[q * 8 + 5] = f2.y; a[q * 8 + 6] = f3.x; a[q * 8 + 7] = f3.y;
-                        }
-                        if (ep.dact == DACT_GELU_NEW) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] *= gelu_new_grad(a[j]);
-                        } else if (ep.dact == DACT_TANH) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] *= (1.0f - a[j] * a[j]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = (a[j] > 0.f) ? v[j] : 0.f;
-                        }
-                    }
-                    __syncwarp();                     // every lane has consumed bufB: fetch the next chunk's operand
-                    if (lane == 0) {
-                        if (c + 1 < nvalid) {
-                            issue_in(tile, c + 1);
-                        } else {
-                            const int tn = next_tile_with_work(tile + tile_step);
-                            if (tn < num_tiles) issue_in(tn, 0);
-                        }
-                    }
-                }
-                if (ep.out != nullptr) {
-                    if (out_f32) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            st_shared_v4(bufA + swz128(lane, q), __float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
-                                         __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            st_shared_v4(bufA + slot_off + swz64(lane, q), pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]),
-                                         pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]),
-                                         pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
-                    }
-                }
-                ptx::fence_proxy_async_smem();        // generic-proxy writes -> visible to the TMA (async proxy)
-                __syncwarp();
-                if (lane == 0) {
-                    if (ep.out != nullptr) tma_store_2d(&maps.out, bufA + slot_off, n0, row0);
-                    if (ep.out2 != nullptr) tma_store_2d(&maps.out2, bufB + slot_off, n0, row0);
-                    tma_store_commit();
-                }
-                ++out_slot;
-            }
-            if (CE && row_ok && n_idx < num_n)
-                ep.ce_partial[static_cast<size_t>(row) * ep.ce_tiles + n_idx * 2 + half] = make_float2(ce_m, ce_s);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
-        }
-        if (lane == 0) tma_store_wait_read<0>();      // staging smem must outlive the last bulk stores
+        epilogue_role<BN, CE>(maps, ep, M, N, num_n, num_tiles, tile_begin, tile_step, coords,
+                              [&](int acc) { ptx::mbar_arrive(tempty_bar + 8 * acc); }, tmem_base, tfull_bar, smem_epi, in_bar0,
+                              warp, lane);
     }
 
     ptx::tcgen05_fence_before();
@@ -501,6 +520,158 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
     if (warp == 1) {
         ptx::tcgen05_fence_after();
         ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// 2-CTA variant: a CTA pair (cluster of 2, adjacent SMs) computes one 256 x BN tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows of A and only HALF of the B tile (BN/2 rows); the pair's tensor cores read both
+// halves, so per CTA the shared-memory traffic per 64-deep K block drops from 2 x (16 + BN/8) KB to 2 x (16 + BN/16) KB
+// (BN = 256: 96 -> 64 KB per 512 MMA clocks) -- the port that capped the 1-CTA kernel at ~55-60 % of the tensor pipe.
+// The leader CTA (rank 0) issues every MMA; both CTAs run producer and epilogue roles on their own rows.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct Cfg2 {
+    static constexpr int STAGE_A = BM * BK * 2;
+    static constexpr int STAGE_B = (BN / 2) * BK * 2;
+    static constexpr int STAGES = (BN == 256) ? 5 : (BN == 192) ? 5 : 6;
+    static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+    static constexpr int EPI_SMEM = EPI_WARPS * 2 * EPI_BUF;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM = STAGES * (STAGE_A + STAGE_B) + EPI_SMEM + BAR_BYTES + 1024;
+    static_assert(BN == 128 || BN == 192 || BN == 256, "pair tile width");
+    static_assert(STAGE_B % 1024 == 0, "B stage must keep 1024-B alignment");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+template <int BN, bool CE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, const GemmEpilogue ep) {
+    using C = Cfg2<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const uint32_t rank = ptx::cluster_ctarank();      // 0 = leader
+    const bool leader = rank == 0;
+
+    const uint32_t smem_a = base;
+    const uint32_t smem_b = base + C::STAGES * C::STAGE_A;
+    const uint32_t smem_epi = smem_b + C::STAGES * C::STAGE_B;
+    const uint32_t bars = smem_epi + C::EPI_SMEM;
+    const uint32_t full_bar = bars;                       // leader's is used: bytes of BOTH CTAs land on it
+    const uint32_t empty_bar = bars + 8 * C::STAGES;      // per CTA: released by the leader's multicast commit
+    const uint32_t tfull_bar = bars + 16 * C::STAGES;     // per CTA: accumulator ready (multicast commit)
+    const uint32_t tempty_bar = tfull_bar + 16;           // leader's is used: 2 x EPI_WARPS arrivals
+    const uint32_t in_bar0 = tempty_bar + 16;
+    const uint32_t tmem_slot = in_bar0 + 8 * EPI_WARPS;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    pdl_trigger();
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&maps.a);
+        ptx::prefetch_tensormap(&maps.b);
+        ptx::prefetch_tensormap(&maps.out);
+        for (int i = 0; i < C::STAGES; ++i) {
+            ptx::mbar_init(full_bar + 8 * i, 1);
+            ptx::mbar_init(empty_bar + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(tfull_bar + 8 * i, 1);
+            ptx::mbar_init(tempty_bar + 8 * i, 2 * EPI_WARPS);
+        }
+        for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(in_bar0 + 8 * i, 1);
+        ptx::fence_barrier_init();
+        ptx::fence_proxy_async_smem();
+    }
+    if (warp == 1) {                                      // the same warp of BOTH CTAs allocates collectively
+        ptx::tmem_alloc_2cta(tmem_slot, C::TMEM_COLS);
+        ptx::tmem_relinquish_2cta();
+    }
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int num_m = (M + BM - 1) / BM;
+    const int num_n = (N + BN - 1) / BN;
+    const int num_pm = (num_m + 1) / 2;                   // pair tiles along M (256 rows)
+    const int num_tiles = num_pm * num_n;
+    const int num_kb = (K + BK - 1) / BK;
+    const int tile_begin = blockIdx.x / 2;
+    const int tile_step = gridDim.x / 2;
+    auto coords = [&](int tile, int& m_idx, int& n_idx) {
+        int pm, pn;
+        tile_coords(tile, num_pm, num_n, pm, pn);
+        m_idx = pm * 2 + static_cast<int>(rank);
+        n_idx = pn;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer (both CTAs) =====================
+            pdl_wait();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
+                int m_idx, n_idx;
+                coords(tile, m_idx, n_idx);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    if (leader) ptx::mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * (C::STAGE_A + C::STAGE_B));
+                    ptx::tma_load_2d_2cta(smem_a + stage * C::STAGE_A, &maps.a, full_bar + 8 * stage, kb * BK, m_idx * BM);
+                    ptx::tma_load_2d_2cta(smem_b + stage * C::STAGE_B, &maps.b, full_bar + 8 * stage, kb * BK,
+                                          n_idx * BN + static_cast<int>(rank) * (BN / 2));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
+                ptx::mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);     // both CTAs' epilogues drained this buffer
+                ptx::tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(full_bar + 8 * stage, phase);          // both CTAs' bytes landed
+                    ptx::tcgen05_fence_after();
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(smem_a + stage * C::STAGE_A);
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(smem_b + stage * C::STAGE_B);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        ptx::umma_bf16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit_2cta(empty_bar + 8 * stage, 0x3);   // frees the slot in both CTAs
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit_2cta(tfull_bar + 8 * acc, 0x3);         // accumulator ready in both CTAs
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+        epilogue_role<BN, CE>(maps, ep, M, N, num_n, num_tiles, tile_begin, tile_step, coords,
+                              [&](int acc) { ptx::mbar_arrive_cluster(tempty_bar + 8 * acc, 0); }, tmem_base, tfull_bar, smem_epi,
+                              in_bar0, warp, lane);
+    }
+
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 1) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -592,14 +763,66 @@ void launch(const GemmArgs& a, cudaStream_t stream) {
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = C::SMEM;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CLUSTER;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, CE, CM, CN>, maps, a.M, a.N, a.K, a.ep));
+    KERNEL_CHECK();
+    if (g_prof_on) {
+        CUDA_CHECK(cudaEventRecord(rec.stop, stream));
+        g_prof.push_back(rec);
+    }
+    g_gemm_launches.fetch_add(1);
+}
+
+template <int BN, bool CE>
+void launch_2cta(const GemmArgs& a, cudaStream_t stream) {
+    using C = Cfg2<BN>;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        configured = true;
+    }
+    const GemmEpilogue& e = a.ep;
+    TmaMaps maps;
+    maps.a = make_map(a.A, a.M, a.K, a.lda, BM, MAP_OPERAND);
+    maps.b = make_map(a.B, a.N, a.K, a.ldb, BN / 2, MAP_OPERAND);      // each CTA of the pair stages half of the B tile
+    maps.out = e.out ? make_map(e.out, a.M, a.N, e.ldo, 32, e.out_fp32 ? MAP_EPI_F32 : MAP_EPI_BF16) : maps.a;
+    maps.out2 = e.out2 ? make_map(e.out2, a.M, a.N, e.ldo2, 32, MAP_EPI_BF16) : maps.a;
+    if (e.residual) maps.in = make_map(e.residual, a.M, a.N, e.ld_res, 32, MAP_EPI_F32);
+    else if (e.dact != DACT_NONE) maps.in = make_map(e.aux, a.M, a.N, e.ld_aux, 32, MAP_EPI_BF16);
+    else maps.in = maps.a;
+    const int tiles = ceil_div(ceil_div(a.M, BM), 2) * ceil_div(a.N, BN);
+    const int max_clusters = num_sms() / 2;
+    const int grid = (tiles < max_clusters ? tiles : max_clusters) * 2;
+    ProfRec rec;
+    if (g_prof_on) {
+        CUDA_CHECK(cudaEventCreate(&rec.start));
+        CUDA_CHECK(cudaEventCreate(&rec.stop));
+        rec.M = a.M; rec.N = a.N; rec.K = a.K; rec.bn = BN + 1000;
+        CUDA_CHECK(cudaEventRecord(rec.start, stream));
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_2cta_kernel<BN, CE>, maps, a.M, a.N, a.K, a.ep));
     KERNEL_CHECK();
     if (g_prof_on) {
         CUDA_CHECK(cudaEventRecord(rec.stop, stream));
@@ -637,19 +860,64 @@ int gemm_pick_block_n(int M, int N, int K, int forced) {
     return best_bn;
 }
 
-// Cluster shape: 1 (none), 2 (2 x 1: B shared) or 4 (2 x 2: A and B shared).  Clusters pay off once there are enough
-// tiles for every cluster to stream several of them; small problems keep independent CTAs (better SM fill).
+// Cluster shape: 1 = independent CTAs, 2 / 4 = 2x1 / 2x2 TMA-multicast clusters (kept for reference: measured no
+// gain, profiles/r01_gemm_cluster_sweep.txt), 8 = CTA pair with tcgen05.mma.cta_group::2 (256 x BN tiles).
+// The pair halves each CTA's shared-memory traffic for B and wins wherever the main loop dominates: measured on
+// B200 (tools/gemm_bench.py) 8192^3 1247 -> 1591 TFLOP/s, LM head 1109 -> 1377, head dgrad 1048 -> 1387,
+// c_fc 1072 -> 1157; it loses on short-K, few-tile problems whose time is epilogue / launch latency.
 int gemm_pick_cluster(int M, int N, int bn, int forced) {
-    if (forced == 1 || forced == 2 || forced == 4) return bn == 64 ? 1 : forced;
-    EAVQA_CHECK(forced == 0, "cluster must be 0, 1, 2 or 4");
-    // Measured on B200 (tools/gemm_bench.py, profiles/r01_gemm_cluster_sweep.txt): 2x1 multicast is within +-5 % of
-    // independent CTAs on every shape of the step and 2x2 is 30-45 % slower (lock-step stalls, stranded SMs), i.e. the
-    // L2 -> SM operand path is not the limiter -- the shared-memory port (TMA writes + UMMA operand reads) is.  Default: none.
-    (void)M; (void)N; (void)bn;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return bn == 64 ? 1 : forced;
+    EAVQA_CHECK(forced == 0, "cluster must be 0, 1, 2, 4 or 8 (8 = CTA pair, tcgen05 cta_group::2)");
+    (void)M; (void)N;
     return 1;
 }
 
-void gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
+// Tile width and CTA mode for a problem.  Model: time ~ waves x (K blocks x clocks per K block + fixed per-tile cost);
+// clocks per 64-deep K block = max(MMA, shared-memory port): 1 CTA max(2 BN, 256 + 2 BN), pair max(2 BN, 256 + BN).
+void gemm_pick_config(int M, int N, int K, int forced_bn, int forced_cluster, int* bn_out, int* cluster_out) {
+    const int sms = num_sms();
+    const int num_m = ceil_div(M, BM);
+    const int kb = ceil_div(K, BK);
+    int cluster = forced_cluster;
+    if (cluster == 0) {
+        const bool many_tiles = static_cast<int64_t>(num_m) * ceil_div(N, 256) >= 4 * sms;
+        const bool long_k = M >= 8192 && K >= 2048;
+        cluster = (many_tiles || long_k) ? 8 : 1;
+    }
+    EAVQA_CHECK(cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8, "cluster must be 0, 1, 2, 4 or 8");
+    int bn = forced_bn;
+    if (bn == 0) {
+        if (cluster == 8) {
+            const int cands[3] = {256, 192, 128};
+            double best = 1e300;
+            for (int i = 0; i < 3; ++i) {
+                const int b = cands[i];
+                const int64_t tiles = static_cast<int64_t>(ceil_div(num_m, 2)) * ceil_div(N, b);
+                const int64_t waves = (tiles + sms / 2 - 1) / (sms / 2);
+                const double per_kb = std::max(2.0 * b, 256.0 + b);
+                const double cost = static_cast<double>(waves) * (kb * per_kb + 700.0);
+                if (cost < best - 1e-9) { best = cost; bn = b; }
+            }
+        } else {
+            bn = gemm_pick_block_n(M, N, K, 0);
+        }
+    }
+    EAVQA_CHECK(bn == 64 || bn == 128 || bn == 192 || bn == 256, "block_n must be 0, 64, 128, 192 or 256");
+    if (bn == 64) cluster = 1;
+    *bn_out = bn;
+    *cluster_out = cluster;
+}
+
+void gemm_bf16_tn(const GemmArgs& a_in, cudaStream_t stream) {
+    GemmArgs a = a_in;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* e = getenv("EAVQA_GEMM_DEBUG");
+            dbg = e ? atoi(e) : 0;
+        }
+        a.ep.debug = dbg;
+    }
     EAVQA_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "GEMM with an empty dimension");
     EAVQA_CHECK(a.A != nullptr && a.B != nullptr, "GEMM operand is null");
     const GemmEpilogue& e = a.ep;
@@ -659,15 +927,16 @@ void gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     EAVQA_CHECK(!(e.residual != nullptr && e.dact != DACT_NONE), "GEMM: residual and derivative operand are exclusive");
     if (e.dact != DACT_NONE) EAVQA_CHECK(e.aux != nullptr, "GEMM: derivative epilogue needs aux");
     const bool ce = e.ce_partial != nullptr;
-    const int bn = gemm_pick_block_n(a.M, a.N, a.K, a.block_n);
+    int bn = 0, cl = 1;
+    gemm_pick_config(a.M, a.N, a.K, a.block_n, a.cluster, &bn, &cl);
     if (ce) {
         EAVQA_CHECK(e.ce_tiles == 2 * ceil_div(a.N, bn), "ce_tiles must be 2 * ceil(N / block_n)");
         EAVQA_CHECK(e.ce_target != nullptr && e.n_valid > 0 && e.n_valid <= a.N, "CE epilogue arguments");
     }
-    const int cl = gemm_pick_cluster(a.M, a.N, bn, a.cluster);
 #define EAVQA_GEMM_CASE(BN_)                                                                   \
     case BN_:                                                                                  \
-        if (cl == 4) ce ? launch<BN_, true, 2, 2>(a, stream) : launch<BN_, false, 2, 2>(a, stream);      \
+        if (cl == 8) ce ? launch_2cta<BN_, true>(a, stream) : launch_2cta<BN_, false>(a, stream);          \
+        else if (cl == 4) ce ? launch<BN_, true, 2, 2>(a, stream) : launch<BN_, false, 2, 2>(a, stream);      \
         else if (cl == 2) ce ? launch<BN_, true, 2, 1>(a, stream) : launch<BN_, false, 2, 1>(a, stream); \
         else ce ? launch<BN_, true, 1, 1>(a, stream) : launch<BN_, false, 1, 1>(a, stream);              \
         break;

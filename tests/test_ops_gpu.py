@@ -76,7 +76,7 @@ def test_gemm_plain_fp32_out(L, shape, block_n):
     assert err <= 2e-3 * math.sqrt(K), f"max err {err} (ref max {ref.abs().max().item()})"
 
 
-@pytest.mark.parametrize("cluster", [2, 4])
+@pytest.mark.parametrize("cluster", [2, 4, 8])   # 8 = CTA pair, tcgen05.mma.cta_group::2 (256 x BN tile)
 @pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 128), (300, 200, 72), (1000, 768, 768), (130, 2304, 768),
                                    (2000, 768, 3072), (5000, 1111 // 8 * 8, 320)], ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("block_n", [128, 192, 256])

@@ -189,3 +189,46 @@ def test_generate_api_shapes_and_errors():
     with pytest.raises(lib.EavqaError):
         model.generate(question_tokens=bad, prefix=batch["clip_embeddings"], question_mask=batch["attention_mask"],
                        max_length=2, pad_token_id=case["pad_token_id"], eos_token_id=case["eos_token_id"])
+
+
+@pytest.mark.parametrize("model_version,mapping_type,clip_dim,batch", [("gpt2-xl", "mlp", 768, 16), ("gpt2-medium", "transformer", 512, 16),
+                                                                        ("gpt2-large", "mlp", 512, 8)])
+def test_large_lm_shapes_run_and_match_a_torch_gpu_reference(model_version, mapping_type, clip_dim, batch):
+    """BASELINE configs[4] shapes (GPT-2 XL: d=1600, 25 heads, 48 layers; 768-d CLIP prefix, MLP mapper) and the other
+    GPT-2 sizes: too slow for the CPU oracle, so the oracle restatement itself is run in fp32 ON THE GPU as the
+    reference (same functions, device tensors).  Same bars as the CPU-oracle cases."""
+    import eavqa_b200
+    import eavqa_b200.synthetic as syn
+    cfg_lm = syn.lm_config(model_version)
+    lm_w = syn.make_lm_weights(cfg_lm, seed=0)
+    mapper_w = syn.make_mapper_params(mapping_type, clip_dim, cfg_lm["d_model"], 10, 10, 8, seed=1, perturb_norm=True)
+    b = syn.make_caption_batch(batch, 24, clip_dim, cfg_lm["vocab"], seed=3, ragged=True)
+    m = eavqa_b200.ClipCaptionPrefixB200(prefix_length=10, clip_length=10, prefix_size=clip_dim, num_layers=8,
+                                         mapping_type=mapping_type, model_version=model_version, lm_state_dict=lm_w)
+    m.clip_project.load_state_dict(mapper_w)
+    m = m.cuda().train()
+    out = m(question_tokens=b["input_ids"], labels=b["labels"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"])
+    out.loss.backward()
+    got = torch.cat([p.grad.flatten() for p in m.parameters()]).double().cpu()
+    loss = float(out.loss.detach())
+    del m
+    torch.cuda.empty_cache()
+    # reference: oracle functions on device tensors (monkey-patching nothing: they are device-agnostic except for the
+    # helper tensors they create, so run under a default-device context)
+    cfg = dict(n_layer=cfg_lm["n_layer"], n_head=cfg_lm["n_head"], d_model=cfg_lm["d_model"], prefix_length=10, clip_length=10,
+               mapping_type=mapping_type, num_layers=8)
+    with torch.device("cuda"):
+        lm_d = {k: v.cuda() for k, v in lm_w.items()}
+        mp_d = {k: v.cuda() for k, v in mapper_w.items()}
+        bd = {k: v.cuda() for k, v in b.items()}
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            loss_o, grads_o = orc.train_step(lm_d, mp_d, cfg, bd["input_ids"], bd["clip_embeddings"], bd["attention_mask"], bd["labels"])
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+    ref = torch.cat([grads_o[k].flatten() for k in grads_o]).double().cpu()
+    cos = float(got @ ref / (got.norm() * ref.norm()))
+    print(f"\n[{model_version}/{mapping_type}] loss {loss:.5f} ref {loss_o:.5f} grad cos {cos:.6f}")
+    assert abs(loss - loss_o) / abs(loss_o) <= LOSS_RTOL
+    assert cos >= GRAD_COS

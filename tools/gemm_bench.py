@@ -35,7 +35,7 @@ shapes = [(12800, 768, 768), (12800, 2304, 768), (12800, 3072, 768), (12800, 768
 for (M, N, K) in shapes:
     row = []
     for bn in (128, 192, 256):
-        for cl in (1, 2, 4):
+        for cl in (1, 8):
             try:
                 ms, tf = run(M, N, K, bn, cl)
                 row.append(f"bn{bn}/c{cl}:{tf:6.0f}")
