@@ -159,6 +159,17 @@ int eavqa_op_gemm(const void* A, int32_t lda, const void* B, int32_t ldb, int32_
     API_END
 }
 
+int eavqa_op_gemm_wgrad(const void* At, int32_t ldat, const void* Bt, int32_t ldbt, int32_t M, int32_t N, int32_t K, float* out,
+                        int32_t ldo, int32_t block_n, void* stream) {
+    API_BEGIN
+    GemmArgs a;
+    a.A = static_cast<const bf16*>(At); a.lda = ldat; a.B = static_cast<const bf16*>(Bt); a.ldb = ldbt;
+    a.M = M; a.N = N; a.K = K; a.block_n = block_n; a.mn_major = 1;
+    a.ep.out = out; a.ep.ldo = ldo; a.ep.out_fp32 = 1;
+    gemm_bf16_tn(a, S(stream));
+    API_END
+}
+
 int eavqa_op_lmhead_ce(const void* H, const void* W, int32_t M, int32_t vocab, int32_t n_cols, int32_t K, const int32_t* label,
                        void* logits, int32_t ldo, float* lse, float* target, float* loss_sum, void* stream) {
     API_BEGIN

@@ -44,6 +44,13 @@ void gemm(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, c
     a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.M = M; a.N = N; a.K = K; a.block_n = bn; a.ep = ep;
     gemm_bf16_tn(a, s);
 }
+// dW[M, N] (fp32) = At^T Bt, At [K, M], Bt [K, N] bf16 row-major: MN-major UMMA operands, no transposed copies
+void gemm_wgrad(const bf16* At, int ldat, const bf16* Bt, int ldbt, int M, int N, int K, float* out, int ldo, cudaStream_t s) {
+    GemmArgs a;
+    a.A = At; a.lda = ldat; a.B = Bt; a.ldb = ldbt; a.M = M; a.N = N; a.K = K; a.mn_major = 1;
+    a.ep.out = out; a.ep.ldo = ldo; a.ep.out_fp32 = 1;
+    gemm_bf16_tn(a, s);
+}
 GemmEpilogue ep_bf16(bf16* out, int ldo, const float* bias = nullptr) {
     GemmEpilogue e;
     e.out = out; e.ldo = ldo; e.out_fp32 = 0; e.bias = bias;
@@ -294,7 +301,7 @@ struct Engine::MapperFwd {
     void plan(Arena& ar, const Engine& e, int N, bool save) {
         const int d = e.d_;
         clip_bf16 = ar.get<bf16>(static_cast<size_t>(N) * e.D_);
-        clip_t = save ? ar.get<bf16>(static_cast<size_t>(e.D_) * pad8(N)) : nullptr;
+        clip_t = nullptr;      // (wgrad reads clip_bf16 directly as an MN-major operand)
         if (e.cfg_.mapper_type == EAVQA_MAPPER_MLP) {
             y1 = ar.get<bf16>(static_cast<size_t>(N) * d * e.P_ / 2);
             y2 = ar.get<float>(static_cast<size_t>(N) * d * e.P_);
@@ -340,7 +347,7 @@ void Engine::pack_mapper_weights(const float* params, bool bwd, MapperW& w, cuda
 void Engine::mapper_forward(const float* params, const MapperW& w, const float* clip, int N, bool save, MapperFwd& f,
                             cudaStream_t s) {
     const int d = d_;
-    convert_transpose_f32(clip, D_, N, D_, f.clip_bf16, D_, f.clip_t, pad8(N), nullptr, s);
+    convert_transpose_f32(clip, D_, N, D_, f.clip_bf16, D_, nullptr, 0, nullptr, s);
     if (cfg_.mapper_type == EAVQA_MAPPER_MLP) {
         // clipcap.py:35-42,256-262: Linear -> Tanh -> Linear
         const int hdim = d * P_ / 2;
@@ -381,81 +388,68 @@ void Engine::mapper_forward(const float* params, const MapperW& w, const float* 
 void Engine::mapper_backward(const float* params, const MapperW& w, const MapperFwd& f, const float* dprefix,
                              int64_t dprefix_batch_stride, int N, float* grads, cudaStream_t s) {
     const int d = d_;
-    const int Np = pad8(N);
     if (cfg_.mapper_type == EAVQA_MAPPER_MLP) {
         const int hdim = d * P_ / 2, out = d * P_;
         bf16* dy2 = arena_.get<bf16>(static_cast<size_t>(N) * out);
-        bf16* dy2_t = arena_.get<bf16>(static_cast<size_t>(out) * Np);
-        bf16* y1_t = arena_.get<bf16>(static_cast<size_t>(hdim) * Np);
         bf16* dy1 = arena_.get<bf16>(static_cast<size_t>(N) * hdim);
-        bf16* dy1_t = arena_.get<bf16>(static_cast<size_t>(hdim) * Np);
         if (grads == nullptr) return;     // planning pass only
-        // dY2 = d loss / d prefix, viewed [N, P*d] (rows of dh with the LM's batch stride)
-        convert_transpose_f32(dprefix, static_cast<int>(dprefix_batch_stride), N, out, dy2, out, dy2_t, Np,
+        // dY2 = d loss / d prefix, viewed [N, P*d] (rows of dh with the LM's batch stride); bias grads = column sums
+        convert_transpose_f32(dprefix, static_cast<int>(dprefix_batch_stride), N, out, dy2, out, nullptr, 0,
                               grads + pofs("model.2.bias"), s);
-        convert_transpose_bf16(f.y1, hdim, N, hdim, y1_t, Np, nullptr, s);
-        gemm(dy2_t, Np, y1_t, Np, out, hdim, N, ep_f32(grads + pofs("model.2.weight"), hdim), s);     // dW2 = dY2^T Y1
+        gemm_wgrad(dy2, out, f.y1, hdim, out, hdim, N, grads + pofs("model.2.weight"), hdim, s);            // dW2 = dY2^T Y1
         GemmEpilogue e = ep_bf16(dy1, hdim);
         e.dact = DACT_TANH; e.aux = f.y1; e.ld_aux = hdim;
-        gemm(dy2, out, w.m2_t, out, N, hdim, out, e, s);                                               // dY1 = (dY2 W2) * tanh'
-        convert_transpose_bf16(dy1, hdim, N, hdim, dy1_t, Np, grads + pofs("model.0.bias"), s);
-        gemm(dy1_t, Np, f.clip_t, Np, hdim, D_, N, ep_f32(grads + pofs("model.0.weight"), D_), s);    // dW1 = dY1^T clip
+        gemm(dy2, out, w.m2_t, out, N, hdim, out, e, s);                                                     // dY1 = (dY2 W2) * tanh'
+        convert_transpose_bf16(dy1, hdim, N, hdim, nullptr, 0, grads + pofs("model.0.bias"), s);
+        gemm_wgrad(dy1, hdim, f.clip_bf16, D_, hdim, D_, N, grads + pofs("model.0.weight"), D_, s);         // dW1 = dY1^T clip
         return;
     }
     const int cl = cfg_.clip_length, S = S_, M2 = N * S, n = cfg_.mapper_layers;
-    const int M2p = pad8(M2);
     const size_t m2 = static_cast<size_t>(M2);
     float* dx = arena_.get<float>(m2 * d);
     bf16* dx_b = arena_.get<bf16>(m2 * d);
-    bf16* dx_t = arena_.get<bf16>(static_cast<size_t>(d) * M2p);
-    bf16* act_t = arena_.get<bf16>(static_cast<size_t>(2 * d) * M2p);     // transposed forward activation (m1 / g / o / a)
     bf16* dm1 = arena_.get<bf16>(m2 * 2 * d);
-    bf16* big_t = arena_.get<bf16>(static_cast<size_t>(3 * d) * M2p);     // dm1^T [2d, M2] / dqkv^T [3d, M2]
     bf16* dsmall = arena_.get<bf16>(m2 * d);                              // dg / d_o / da
     bf16* dqkv = arena_.get<bf16>(m2 * 3 * d);
-    bf16* dlin_t = arena_.get<bf16>(static_cast<size_t>(cl) * d * Np);
+    bf16* dlin = arena_.get<bf16>(static_cast<size_t>(N) * cl * d);
     if (grads == nullptr) return;         // planning pass only
     {
         const int64_t total = static_cast<int64_t>(M2) * (d / 4);
-        launch_kernel(scatter_prefix_grad_kernel, dim3(static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 8))), dim3(256), 0, s, 
-            reinterpret_cast<const float4*>(dprefix), dprefix_batch_stride / 4, reinterpret_cast<float4*>(dx), N, S, cl, d / 4);
+        launch_kernel(scatter_prefix_grad_kernel, dim3(static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 8))), dim3(256), 0, s,
+                      reinterpret_cast<const float4*>(dprefix), dprefix_batch_stride / 4, reinterpret_cast<float4*>(dx), N, S, cl, d / 4);
         KERNEL_CHECK();
         count_launch();
     }
+    // every weight gradient dW = dY^T X reads dY and X as stored ([rows, features]) through MN-major UMMA descriptors
     for (int l = n - 1; l >= 0; --l) {
         const std::string p = "transformer.layers." + std::to_string(l) + ".";
         // ---- MLP branch: x2 = x1 + fc2(relu(fc1(LN2(x1))))   (clipcap.py:61-67,116)
-        convert_transpose_f32(dx, d, M2, d, dx_b, d, dx_t, M2p, grads + pofs(p + "mlp.fc2.bias"), s);
-        convert_transpose_bf16(f.m1[l], 2 * d, M2, 2 * d, act_t, M2p, nullptr, s);
-        gemm(dx_t, M2p, act_t, M2p, d, 2 * d, M2, ep_f32(grads + pofs(p + "mlp.fc2.weight"), 2 * d), s);   // dW2 = dx^T m1
+        convert_transpose_f32(dx, d, M2, d, dx_b, d, nullptr, 0, grads + pofs(p + "mlp.fc2.bias"), s);
+        gemm_wgrad(dx_b, d, f.m1[l], 2 * d, d, 2 * d, M2, grads + pofs(p + "mlp.fc2.weight"), 2 * d, s);  // dW2 = dx^T m1
         {
             GemmEpilogue e = ep_bf16(dm1, 2 * d);
             e.dact = DACT_RELU; e.aux = f.m1[l]; e.ld_aux = 2 * d;
             gemm(dx_b, d, w.w2_t[l], d, M2, 2 * d, d, e, s);                                               // dm1 = (dx W2) * relu'
         }
-        convert_transpose_bf16(dm1, 2 * d, M2, 2 * d, big_t, M2p, grads + pofs(p + "mlp.fc1.bias"), s);
-        convert_transpose_bf16(f.g[l], d, M2, d, act_t, M2p, nullptr, s);
-        gemm(big_t, M2p, act_t, M2p, 2 * d, d, M2, ep_f32(grads + pofs(p + "mlp.fc1.weight"), d), s);      // dW1 = dm1^T g
+        convert_transpose_bf16(dm1, 2 * d, M2, 2 * d, nullptr, 0, grads + pofs(p + "mlp.fc1.bias"), s);
+        gemm_wgrad(dm1, 2 * d, f.g[l], d, 2 * d, d, M2, grads + pofs(p + "mlp.fc1.weight"), d, s);        // dW1 = dm1^T g
         gemm(dm1, 2 * d, w.w1_t[l], 2 * d, M2, d, 2 * d, ep_bf16(dsmall, d), s);                          // dg = dm1 W1
         layernorm_bwd(dsmall, d, f.x[2 * l + 1], d, nullptr, params + pofs(p + "norm2.weight"), f.mean2[l], f.rstd2[l], dx, d,
                       1, nullptr, 0, grads + pofs(p + "norm2.weight"), grads + pofs(p + "norm2.bias"), M2, d, 1e-5f, s);
         // ---- attention branch: x1 = x0 + project(attn(LN1(x0)))   (clipcap.py:81-104,115)
-        convert_transpose_f32(dx, d, M2, d, dx_b, d, dx_t, M2p, grads + pofs(p + "attn.project.bias"), s);
-        convert_transpose_bf16(f.o[l], d, M2, d, act_t, M2p, nullptr, s);
-        gemm(dx_t, M2p, act_t, M2p, d, d, M2, ep_f32(grads + pofs(p + "attn.project.weight"), d), s);      // dWp = dx^T o
+        convert_transpose_f32(dx, d, M2, d, dx_b, d, nullptr, 0, grads + pofs(p + "attn.project.bias"), s);
+        gemm_wgrad(dx_b, d, f.o[l], d, d, d, M2, grads + pofs(p + "attn.project.weight"), d, s);          // dWp = dx^T o
         gemm(dx_b, d, w.wp_t[l], d, M2, d, d, ep_bf16(dsmall, d), s);                                     // d_o = dx Wp
         mapper_attention_bwd(f.qkv[l], dsmall, dqkv, N, S, 8, d / 8, s);
-        convert_transpose_bf16(dqkv, 3 * d, M2, 3 * d, big_t, M2p, nullptr, s);
-        convert_transpose_bf16(f.a[l], d, M2, d, act_t, M2p, nullptr, s);
-        gemm(big_t, M2p, act_t, M2p, 3 * d, d, M2, ep_f32(grads + pofs(p + "attn.to_queries.weight"), d), s);   // d[Wq;Wkv] = dqkv^T a
+        gemm_wgrad(dqkv, 3 * d, f.a[l], d, 3 * d, d, M2, grads + pofs(p + "attn.to_queries.weight"), d, s);   // d[Wq;Wkv] = dqkv^T a
         gemm(dqkv, 3 * d, w.wqkv_t[l], 3 * d, M2, d, 3 * d, ep_bf16(dsmall, d), s);                       // da = dqkv [Wq;Wkv]
         layernorm_bwd(dsmall, d, f.x[2 * l], d, nullptr, params + pofs(p + "norm1.weight"), f.mean1[l], f.rstd1[l], dx, d, 1,
                       nullptr, 0, grads + pofs(p + "norm1.weight"), grads + pofs(p + "norm1.bias"), M2, d, 1e-5f, s);
     }
     // x0 = cat(linear(clip).view(N, cl, d), prefix_const)
     sum_over_batch_f32(dx + static_cast<size_t>(cl) * d, static_cast<int64_t>(S) * d, N, P_ * d, grads + pofs("prefix_const"), s);
-    convert_transpose_f32(dx, S * d, N, cl * d, nullptr, 0, dlin_t, Np, grads + pofs("linear.bias"), s);
-    gemm(dlin_t, Np, f.clip_t, Np, cl * d, D_, N, ep_f32(grads + pofs("linear.weight"), D_), s);           // dWl = dlin^T clip
+    convert_transpose_f32(dx, S * d, N, cl * d, dlin, cl * d, nullptr, 0, grads + pofs("linear.bias"), s);
+    gemm_wgrad(dlin, cl * d, f.clip_bf16, D_, cl * d, D_, N, grads + pofs("linear.weight"), D_, s);        // dWl = dlin^T clip
 }
 
 // ============================================================================================ LM block

@@ -45,6 +45,9 @@ struct GemmArgs {
     const bf16* B = nullptr;
     int lda = 0, ldb = 0;            // row strides in elements (multiples of 8)
     int M = 0, N = 0, K = 0;
+    // "wgrad form": D[M, N] = At^T * Bt with At [K, M] and Bt [K, N] row-major (contraction over their ROWS), read as
+    // MN-major UMMA operands -- no transposed copies.  A / B then point at At / Bt and lda / ldb are their row strides.
+    int mn_major = 0;
     int block_n = 0;                 // 0 = pick by wave-quantisation heuristic; else 64/128/192/256
     int cluster = 0;                 // 0 = heuristic; 1 = single CTAs; 8 = CTA pair (cta_group::2); 2 / 4 = multicast clusters
     GemmEpilogue ep;

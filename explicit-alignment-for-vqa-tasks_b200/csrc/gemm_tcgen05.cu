@@ -370,11 +370,12 @@ __device__ __forceinline__ void epilogue_role(const TmaMaps& maps, const GemmEpi
 // byte crosses the L2 -> SM fabric once per cluster instead of once per CTA.  (Round-1 measurement: with single
 // CTAs the 128x192 tile needs 40 KB per 64-deep K block, and L2 delivers ~46 B/clk/SM -> ~890 clk per K block
 // against 384 clk of MMA: every large GEMM plateaued at ~1000 TFLOP/s.)
-template <int BN, bool CE, int CM, int CN>
+template <int BN, bool CE, int CM, int CN, bool MN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, const GemmEpilogue ep) {
     using C = Cfg<BN>;
     constexpr int CLUSTER = CM * CN;
+    static_assert(!MN || CLUSTER == 1, "MN-major operands are implemented for independent CTAs only");
     const uint32_t crank = CLUSTER > 1 ? ptx::cluster_ctarank() : 0u;
     const int cm = crank % CM, cn = crank / CM;
     // peers that share my A tile (same cm) / my B tile (same cn), as cluster-rank bit masks
@@ -461,12 +462,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1);           // the slot is free here AND in every peer
                     ptx::mbar_arrive_expect_tx(full_bar + 8 * stage, C::STAGE_A + C::STAGE_B);
-                    if (CN == 1)
+                    if (MN) {
+                        // operands stored [K, MN]: boxes of 64 (MN) x 64 (K rows), one per 64 columns of the tile
+#pragma unroll
+                        for (int bx = 0; bx < BM / 64; ++bx)
+                            ptx::tma_load_2d(smem_a + stage * C::STAGE_A + bx * 8192, &maps.a, full_bar + 8 * stage,
+                                             m_idx * BM + bx * 64, kb * BK);
+#pragma unroll
+                        for (int bx = 0; bx < BN / 64; ++bx)
+                            ptx::tma_load_2d(smem_b + stage * C::STAGE_B + bx * 8192, &maps.b, full_bar + 8 * stage,
+                                             n_idx * BN + bx * 64, kb * BK);
+                    } else if (CN == 1)
                         ptx::tma_load_2d(smem_a + stage * C::STAGE_A, &maps.a, full_bar + 8 * stage, kb * BK, m_idx * BM);
                     else
                         ptx::tma_load_2d_multicast(smem_a + stage * C::STAGE_A + cn * (C::STAGE_A / CN), &maps.a,
                                                    full_bar + 8 * stage, kb * BK, m_idx * BM + cn * (BM / CN), mask_a);
-                    if (CM == 1)
+                    if (MN) {
+                    } else if (CM == 1)
                         ptx::tma_load_2d(smem_b + stage * C::STAGE_B, &maps.b, full_bar + 8 * stage, kb * BK, n_idx * BN);
                     else
                         ptx::tma_load_2d_multicast(smem_b + stage * C::STAGE_B + cm * (C::STAGE_B / CM), &maps.b,
@@ -478,7 +490,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
     } else if (warp == 1) {
         if (lane == 0) {
             // ===================== MMA issuer =====================
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN, MN, MN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -490,12 +502,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(full_bar + 8 * stage, phase);          // TMA bytes landed
                     ptx::tcgen05_fence_after();
-                    const uint64_t da = ptx::make_kmajor_sw128_desc(smem_a + stage * C::STAGE_A);
-                    const uint64_t db = ptx::make_kmajor_sw128_desc(smem_b + stage * C::STAGE_B);
+                    const uint64_t da = MN ? ptx::make_mnmajor_sw128_desc(smem_a + stage * C::STAGE_A)
+                                           : ptx::make_kmajor_sw128_desc(smem_a + stage * C::STAGE_A);
+                    const uint64_t db = MN ? ptx::make_mnmajor_sw128_desc(smem_b + stage * C::STAGE_B)
+                                           : ptx::make_kmajor_sw128_desc(smem_b + stage * C::STAGE_B);
+                    // one UMMA_K = 16 step: K-major +32 B inside the 128-B swizzle row; MN-major +16 rows = 2048 B
+                    constexpr uint32_t kstep = MN ? (2048u >> 4) : (32u >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advancing 16 bf16 (32 B) along K inside the 128-B swizzle row: +2 in the >>4 address field
-                        ptx::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_bf16(tmem_d, da + kstep * k, db + kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     // frees the smem slot (here and for the peers that multicast into it) when the MMAs retire
                     if (CLUSTER == 1) ptx::umma_commit(empty_bar + 8 * stage);
@@ -730,19 +745,25 @@ CUtensorMap make_map(const void* ptr, int rows, int cols, int ld, int box_rows, 
     return m;
 }
 
-template <int BN, bool CE, int CM, int CN>
+template <int BN, bool CE, int CM, int CN, bool MN = false>
 void launch(const GemmArgs& a, cudaStream_t stream) {
     using C = Cfg<BN>;
     constexpr int CLUSTER = CM * CN;
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, CE, CM, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, CE, CM, CN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
     const GemmEpilogue& e = a.ep;
     TmaMaps maps;
-    maps.a = make_map(a.A, a.M, a.K, a.lda, BM / CN, MAP_OPERAND);      // each CTA fetches its 1/CN slice of the A tile
-    maps.b = make_map(a.B, a.N, a.K, a.ldb, BN / CM, MAP_OPERAND);      // ... and its 1/CM slice of the B tile
+    if (MN) {
+        // At [K, M] / Bt [K, N] row-major: rows = contraction index, 64-column x 64-row boxes
+        maps.a = make_map(a.A, a.K, a.M, a.lda, 64, MAP_OPERAND);
+        maps.b = make_map(a.B, a.K, a.N, a.ldb, 64, MAP_OPERAND);
+    } else {
+        maps.a = make_map(a.A, a.M, a.K, a.lda, BM / CN, MAP_OPERAND);  // each CTA fetches its 1/CN slice of the A tile
+        maps.b = make_map(a.B, a.N, a.K, a.ldb, BN / CM, MAP_OPERAND);  // ... and its 1/CM slice of the B tile
+    }
     maps.out = e.out ? make_map(e.out, a.M, a.N, e.ldo, 32, e.out_fp32 ? MAP_EPI_F32 : MAP_EPI_BF16) : maps.a;
     maps.out2 = e.out2 ? make_map(e.out2, a.M, a.N, e.ldo2, 32, MAP_EPI_BF16) : maps.a;
     if (e.residual) maps.in = make_map(e.residual, a.M, a.N, e.ld_res, 32, MAP_EPI_F32);
@@ -772,7 +793,7 @@ void launch(const GemmArgs& a, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, CE, CM, CN>, maps, a.M, a.N, a.K, a.ep));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, CE, CM, CN, MN>, maps, a.M, a.N, a.K, a.ep));
     KERNEL_CHECK();
     if (g_prof_on) {
         CUDA_CHECK(cudaEventRecord(rec.stop, stream));
@@ -928,7 +949,7 @@ void gemm_bf16_tn(const GemmArgs& a_in, cudaStream_t stream) {
     if (e.dact != DACT_NONE) EAVQA_CHECK(e.aux != nullptr, "GEMM: derivative epilogue needs aux");
     const bool ce = e.ce_partial != nullptr;
     int bn = 0, cl = 1;
-    gemm_pick_config(a.M, a.N, a.K, a.block_n, a.cluster, &bn, &cl);
+    gemm_pick_config(a.M, a.N, a.K, a.block_n, a.mn_major ? 1 : a.cluster, &bn, &cl);
     if (ce) {
         EAVQA_CHECK(e.ce_tiles == 2 * ceil_div(a.N, bn), "ce_tiles must be 2 * ceil(N / block_n)");
         EAVQA_CHECK(e.ce_target != nullptr && e.n_valid > 0 && e.n_valid <= a.N, "CE epilogue arguments");
@@ -940,6 +961,16 @@ void gemm_bf16_tn(const GemmArgs& a_in, cudaStream_t stream) {
         else if (cl == 2) ce ? launch<BN_, true, 2, 1>(a, stream) : launch<BN_, false, 2, 1>(a, stream); \
         else ce ? launch<BN_, true, 1, 1>(a, stream) : launch<BN_, false, 1, 1>(a, stream);              \
         break;
+    if (a.mn_major) {
+        EAVQA_CHECK(!ce && cl == 1, "MN-major (wgrad form) GEMM: plain epilogues, independent CTAs only");
+        switch (bn) {
+            case 256: launch<256, false, 1, 1, true>(a, stream); break;
+            case 192: launch<192, false, 1, 1, true>(a, stream); break;
+            case 128: launch<128, false, 1, 1, true>(a, stream); break;
+            default: launch<64, false, 1, 1, true>(a, stream); break;
+        }
+        return;
+    }
     switch (bn) {
         EAVQA_GEMM_CASE(256)
         EAVQA_GEMM_CASE(192)

@@ -184,11 +184,25 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// MN-major operand (the contraction index is the slow one in memory: X^T of a row-major X), staged by TMA as
+// boxes of 64 (MN, contiguous, 128 B) x 64 (K rows) with SWIZZLE_128B, consecutive boxes along MN 8192 B apart.
+// The swizzle atom is 64 (MN) x 8 (K): stride between atoms along K = 8 rows x 128 B = 1024 B (SBO field),
+// stride between atoms along MN = one box = 8192 B (LBO field).  One UMMA_K = 16 step advances 16 rows = 2048 B.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>(8192u >> 4) << 16;
+    d |= static_cast<uint64_t>(1024u >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B (both K-major) and fp32 D:
 // [4,6) D format = 1 (f32); [7,10) A format = 1 (bf16); [10,13) B format = 1 (bf16);
 // [15] A major = 0 (K); [16] B major = 0 (K); [17,23) N >> 3; [24,29) M >> 4.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n, bool a_mn_major = false, bool b_mn_major = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u) |
+           (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 }  // namespace ptx

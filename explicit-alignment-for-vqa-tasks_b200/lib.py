@@ -52,6 +52,8 @@ PROTOTYPES = {
     "eavqa_op_gemm": (C.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32,
                                 c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32,
                                 c_void_p]),
+    "eavqa_op_gemm_wgrad": (C.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32,
+                                      c_void_p]),
     "eavqa_op_lmhead_ce": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "eavqa_op_layernorm_fwd": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),

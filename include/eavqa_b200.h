@@ -122,6 +122,10 @@ int eavqa_profile_end(double* total_ms, double* total_flops, int64_t* launches, 
 int eavqa_op_gemm(const void* A, int32_t lda, const void* B, int32_t ldb, int32_t M, int32_t N, int32_t K, void* out,
                   int32_t ldo, int32_t out_fp32, const float* bias, const float* residual, int32_t ld_res, int32_t act,
                   const void* aux, int32_t ld_aux, int32_t dact, void* out2, int32_t ldo2, int32_t block_n, void* stream);
+/* weight-gradient form D[M,N] (fp32) = At^T * Bt, At [K,M] and Bt [K,N] bf16 row-major (contraction over rows):
+ * read as MN-major UMMA operands, no transposed copies (dW = dY^T X of every trainable nn.Linear) */
+int eavqa_op_gemm_wgrad(const void* At, int32_t ldat, const void* Bt, int32_t ldbt, int32_t M, int32_t N, int32_t K, float* out,
+                        int32_t ldo, int32_t block_n, void* stream);
 /* LM-head GEMM with fused softmax statistics: logits bf16 [M, ldo], lse [M] and target logit [M] */
 int eavqa_op_lmhead_ce(const void* H, const void* W, int32_t M, int32_t vocab, int32_t n_cols, int32_t K, const int32_t* label,
                        void* logits, int32_t ldo, float* lse, float* target, float* loss_sum, void* stream);

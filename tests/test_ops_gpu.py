@@ -97,6 +97,22 @@ def test_gemm_clusters_tma_multicast(L, shape, block_n, cluster):
     assert (out2.float() - pre).abs().max().item() <= 2e-3 * math.sqrt(K) + 2 ** -8 * pre.abs().max().item()
 
 
+@pytest.mark.parametrize("shape", [(128, 64, 64), (128, 128, 128), (768, 768, 5120), (2304, 768, 5120), (7680, 512, 256),
+                                   (200, 136, 72), (3840, 512, 8), (768, 1536, 100)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("block_n", [0, 64, 128, 192, 256])
+def test_gemm_wgrad_mn_major_operands(L, shape, block_n):
+    """dW[M,N] = At^T Bt with At [K,M], Bt [K,N] row-major: MN-major UMMA descriptors, no transposed copies."""
+    M, N, K = shape
+    At = _rand((K, M), 1, dtype=torch.bfloat16)
+    Bt = _rand((K, N), 2, dtype=torch.bfloat16)
+    out = torch.zeros(M, N, device="cuda")
+    _check(L.eavqa_op_gemm_wgrad(At.data_ptr(), M, Bt.data_ptr(), N, M, N, K, out.data_ptr(), N, block_n, _stream()))
+    torch.cuda.synchronize()
+    ref = At.float().t() @ Bt.float()
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * math.sqrt(K), f"max err {err} (ref max {ref.abs().max().item()})"
+
+
 def test_gemm_identity_exposes_layout(L):
     """B = I: the output must reproduce A exactly (bf16 values are exact in fp32) -- catches any swizzle /
     descriptor / TMEM-lane mix-up as a permutation."""
