@@ -164,8 +164,9 @@ int eavqa_op_gemm_wgrad(const void* At, int32_t ldat, const void* Bt, int32_t ld
     API_BEGIN
     GemmArgs a;
     a.A = static_cast<const bf16*>(At); a.lda = ldat; a.B = static_cast<const bf16*>(Bt); a.ldb = ldbt;
-    a.M = M; a.N = N; a.K = K; a.block_n = block_n; a.mn_major = 1;
+    a.M = M; a.N = N; a.K = K; a.block_n = block_n % 1000; a.mn_major = 1;
     a.ep.out = out; a.ep.ldo = ldo; a.ep.out_fp32 = 1;
+    a.ep.split_k = block_n / 1000;        // > 1: partials are ADDED into `out` (caller zero-initialises)
     gemm_bf16_tn(a, S(stream));
     API_END
 }

@@ -49,6 +49,15 @@ void gemm_wgrad(const bf16* At, int ldat, const bf16* Bt, int ldbt, int M, int N
     GemmArgs a;
     a.A = At; a.lda = ldat; a.B = Bt; a.ldb = ldbt; a.M = M; a.N = N; a.K = K; a.mn_major = 1;
     a.ep.out = out; a.ep.ldo = ldo; a.ep.out_fp32 = 1;
+    // weight gradients are few-tile, long-K problems (e.g. 768 x 768 x 5120: 36 tiles for 148 SMs): split K so that
+    // ~2 CTAs per SM stream it, each ADDING its fp32 partial into the gradient buffer (zeroed at the top of the step)
+    const int bn = N >= 128 ? 128 : 64;       // 128-wide tiles keep the main loop off the shared-memory port limit
+    const int tiles = ceil_div(M, 128) * ceil_div(N, bn);
+    const int kb = ceil_div(K, 64);
+    int split = (2 * num_sms()) / std::max(tiles, 1);
+    split = std::max(1, std::min(split, std::min(8, kb / 4)));
+    a.block_n = bn;
+    a.ep.split_k = split;
     gemm_bf16_tn(a, s);
 }
 GemmEpilogue ep_bf16(bf16* out, int ldo, const float* bias = nullptr) {

@@ -36,6 +36,8 @@ struct GemmEpilogue {
     const int* ce_label = nullptr;   // [M], -1 = none
     int ce_tiles = 0;
     int n_valid = 0;
+    int split_k = 1;                 // > 1: K is split over `split_k` CTAs per output tile which ADD their fp32 partials
+                                     // into `out` (TMA reduce-add; out must be pre-initialised; plain fp32 epilogue only)
     int debug = 0;                   // EAVQA_GEMM_DEBUG (timing experiments only; results are wrong when non-zero):
                                      // 1 = issue every other TMA store, 2 = no TMA stores, 3 = no staging and no stores
 };

@@ -126,6 +126,10 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -351,7 +355,10 @@ __device__ __forceinline__ void epilogue_role(const TmaMaps& maps, const GemmEpi
             ptx::fence_proxy_async_smem();        // generic-proxy writes -> visible to the TMA (async proxy)
             __syncwarp();
             if (lane == 0 && !(ep.debug == 2 || ep.debug == 3 || (ep.debug == 1 && (out_slot & 1)))) {
-                if (ep.out != nullptr) tma_store_2d(&maps.out, bufA + slot_off, n0, row0);
+                if (ep.out != nullptr) {
+                    if (ep.split_k > 1) tma_reduce_add_2d(&maps.out, bufA + slot_off, n0, row0);
+                    else tma_store_2d(&maps.out, bufA + slot_off, n0, row0);
+                }
                 if (ep.out2 != nullptr) tma_store_2d(&maps.out2, bufB + slot_off, n0, row0);
                 tma_store_commit();
             }
@@ -439,15 +446,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
     // past the edge are computed on zero-filled operands and clipped by the TMA stores.
     const int num_sm = (num_m + CM - 1) / CM;
     const int num_sn = (num_n + CN - 1) / CN;
-    const int num_tiles = num_sm * num_sn;
+    const int split = ep.split_k > 1 ? ep.split_k : 1;      // split-K: `split` consecutive work items share an output tile
+    const int num_tiles = num_sm * num_sn * split;
     const int num_kb = (K + BK - 1) / BK;
     const int tile_begin = blockIdx.x / CLUSTER;
     const int tile_step = gridDim.x / CLUSTER;
     auto coords = [&](int tile, int& m_idx, int& n_idx) {
         int sm, sn;
-        tile_coords(tile, num_sm, num_sn, sm, sn);
+        tile_coords(tile / split, num_sm, num_sn, sm, sn);
         m_idx = sm * CM + cm;
         n_idx = sn * CN + cn;
+    };
+    auto kb_range = [&](int tile, int& kb0, int& kb1) {     // balanced, never empty (split <= num_kb)
+        const int sp = tile % split;
+        kb0 = static_cast<int>(static_cast<int64_t>(sp) * num_kb / split);
+        kb1 = static_cast<int>(static_cast<int64_t>(sp + 1) * num_kb / split);
     };
 
     if (warp == 0) {
@@ -457,9 +470,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
-                int m_idx, n_idx;
+                int m_idx, n_idx, kb0, kb1;
                 coords(tile, m_idx, n_idx);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                kb_range(tile, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1);           // the slot is free here AND in every peer
                     ptx::mbar_arrive_expect_tx(full_bar + 8 * stage, C::STAGE_A + C::STAGE_B);
                     if (MN) {
@@ -499,7 +513,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
                 ptx::mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);     // epilogue drained this buffer
                 ptx::tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                int kb0, kb1;
+                kb_range(tile, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(full_bar + 8 * stage, phase);          // TMA bytes landed
                     ptx::tcgen05_fence_after();
                     const uint64_t da = MN ? ptx::make_mnmajor_sw128_desc(smem_a + stage * C::STAGE_A)
@@ -510,7 +526,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
                     constexpr uint32_t kstep = MN ? (2048u >> 4) : (32u >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        ptx::umma_bf16(tmem_d, da + kstep * k, db + kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_bf16(tmem_d, da + kstep * k, db + kstep * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
                     // frees the smem slot (here and for the peers that multicast into it) when the MMAs retire
                     if (CLUSTER == 1) ptx::umma_commit(empty_bar + 8 * stage);
@@ -769,7 +785,8 @@ void launch(const GemmArgs& a, cudaStream_t stream) {
     if (e.residual) maps.in = make_map(e.residual, a.M, a.N, e.ld_res, 32, MAP_EPI_F32);
     else if (e.dact != DACT_NONE) maps.in = make_map(e.aux, a.M, a.N, e.ld_aux, 32, MAP_EPI_BF16);
     else maps.in = maps.a;
-    const int tiles = ceil_div(ceil_div(a.M, BM), CM) * ceil_div(ceil_div(a.N, BN), CN);      // super tiles
+    const int split = e.split_k > 1 ? e.split_k : 1;
+    const int tiles = ceil_div(ceil_div(a.M, BM), CM) * ceil_div(ceil_div(a.N, BN), CN) * split;      // super tiles x K splits
     const int max_clusters = num_sms() / CLUSTER;
     const int grid = (tiles < max_clusters ? tiles : max_clusters) * CLUSTER;
     ProfRec rec;
@@ -961,6 +978,11 @@ void gemm_bf16_tn(const GemmArgs& a_in, cudaStream_t stream) {
         else if (cl == 2) ce ? launch<BN_, true, 2, 1>(a, stream) : launch<BN_, false, 2, 1>(a, stream); \
         else ce ? launch<BN_, true, 1, 1>(a, stream) : launch<BN_, false, 1, 1>(a, stream);              \
         break;
+    if (a.ep.split_k > 1) {
+        EAVQA_CHECK(e.out != nullptr && e.out_fp32 && !e.bias && !e.residual && !e.out2 && e.act == ACT_NONE && e.dact == DACT_NONE && !ce,
+                    "split-K needs a plain fp32 output (partials are added into it)");
+        EAVQA_CHECK(cl == 1 && a.ep.split_k <= ceil_div(a.K, BK), "split-K: independent CTAs, at most one split per K block");
+    }
     if (a.mn_major) {
         EAVQA_CHECK(!ce && cl == 1, "MN-major (wgrad form) GEMM: plain epilogues, independent CTAs only");
         switch (bn) {

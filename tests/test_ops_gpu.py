@@ -113,6 +113,21 @@ def test_gemm_wgrad_mn_major_operands(L, shape, block_n):
     assert err <= 2e-3 * math.sqrt(K), f"max err {err} (ref max {ref.abs().max().item()})"
 
 
+@pytest.mark.parametrize("split", [2, 3, 8])
+@pytest.mark.parametrize("shape", [(768, 768, 5120), (2304, 768, 5120), (200, 136, 1000), (3840, 512, 520)], ids=lambda s: "x".join(map(str, s)))
+def test_gemm_wgrad_split_k_reduce_add(L, shape, split):
+    """split-K: each split ADDS its fp32 partial into the output with a TMA reduce (cp.reduce.async.bulk.tensor)."""
+    M, N, K = shape
+    At = _rand((K, M), 1, dtype=torch.bfloat16)
+    Bt = _rand((K, N), 2, dtype=torch.bfloat16)
+    init = _rand((M, N), 3)
+    out = init.clone()
+    _check(L.eavqa_op_gemm_wgrad(At.data_ptr(), M, Bt.data_ptr(), N, M, N, K, out.data_ptr(), N, 128 + 1000 * split, _stream()))
+    torch.cuda.synchronize()
+    ref = init + At.float().t() @ Bt.float()
+    assert (out - ref).abs().max().item() <= 2e-3 * math.sqrt(K)
+
+
 def test_gemm_identity_exposes_layout(L):
     """B = I: the output must reproduce A exactly (bf16 values are exact in fp32) -- catches any swizzle /
     descriptor / TMEM-lane mix-up as a permutation."""
