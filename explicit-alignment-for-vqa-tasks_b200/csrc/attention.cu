@@ -69,6 +69,23 @@ __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t ld
     }
 }
 
+// same, through cp.async (no register staging: every 16-byte request of the tile is in flight at once)
+__device__ __forceinline__ void load_tile_async(bf16* dst, const bf16* src, int64_t ld, int row0, int nrows, int tid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = tid + 128 * i;
+        const int r = idx >> 3, c = (idx & 7) * 8;
+        bf16* d = dst + r * LDS + c;
+        if (row0 + r < nrows) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(d)),
+                         "l"(src + static_cast<int64_t>(row0 + r) * ld + c) : "memory");
+        } else {
+            *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // S(16 x 64 per warp) = A(16 x 64, fragments af) * X[n][k]^T
 __device__ __forceinline__ void warp_gemm_nt(float (&acc)[8][4], const uint32_t (&af)[4][4], const bf16* xtile, int lane) {
 #pragma unroll
@@ -101,7 +118,12 @@ __global__ void __launch_bounds__(128, 4) lm_attention_fwd_kernel(const bf16* __
     const int q0 = qb * BLK;
     const float scale = 0.125f;     // head_dim ** -0.5  (HF modeling_gpt2.py:96-98)
 
-    load_tile(Qs, base, ld, q0, T, tid);
+    // Q and the first K/V block are requested together (for T <= 64 that is everything the CTA ever loads)
+    load_tile_async(Qs, base, ld, q0, T, tid);
+    load_tile_async(Ks, base + d, ld, 0, T, tid);
+    load_tile_async(Vs, base + 2 * d, ld, 0, T, tid);
+    if (tid < BLK) kvalid[tid] = (tid < T) ? valid[b * T + tid] : 0;
+    cp_async_wait_all();
     __syncthreads();
     uint32_t qf[4][4];
 #pragma unroll
@@ -116,11 +138,14 @@ __global__ void __launch_bounds__(128, 4) lm_attention_fwd_kernel(const bf16* __
 
     for (int kb = 0; kb <= qb; ++kb) {
         const int k0 = kb * BLK;
-        __syncthreads();
-        load_tile(Ks, base + d, ld, k0, T, tid);
-        load_tile(Vs, base + 2 * d, ld, k0, T, tid);
-        if (tid < BLK) kvalid[tid] = (k0 + tid < T) ? valid[b * T + k0 + tid] : 0;
-        __syncthreads();
+        if (kb > 0) {
+            __syncthreads();
+            load_tile_async(Ks, base + d, ld, k0, T, tid);
+            load_tile_async(Vs, base + 2 * d, ld, k0, T, tid);
+            if (tid < BLK) kvalid[tid] = (k0 + tid < T) ? valid[b * T + k0 + tid] : 0;
+            cp_async_wait_all();
+            __syncthreads();
+        }
 
         float sacc[8][4];
 #pragma unroll
@@ -417,26 +442,27 @@ __global__ void __launch_bounds__(128, 4) lm_attention_bwd_single_kernel(const b
     bf16* dbase = dqkv + static_cast<int64_t>(b) * T * ld + h * HD;
     const float scale = 0.125f;
 
-    load_tile(Qs, base, ld, 0, T, tid);
-    load_tile(Ks, base + d, ld, 0, T, tid);
-    load_tile(Vs, base + 2 * d, ld, 0, T, tid);
-    load_tile(dOs, dobase, d, 0, T, tid);
+    load_tile_async(Qs, base, ld, 0, T, tid);
+    load_tile_async(Ks, base + d, ld, 0, T, tid);
+    load_tile_async(Vs, base + 2 * d, ld, 0, T, tid);
+    load_tile_async(dOs, dobase, d, 0, T, tid);
+    load_tile_async(Ps, obase, d, 0, T, tid);          // O, only needed for D; Ps is overwritten with P afterwards
     if (tid < BLK) kvalid[tid] = (tid < T) ? valid[b * T + tid] : 0;
+    cp_async_wait_all();
+    __syncthreads();
     {   // D = rowsum(dO * O), lse: two threads per query row
         const int r = tid >> 1, half = tid & 1;
         float acc = 0.f;
-        if (r < T) {
-            const uint4* op = reinterpret_cast<const uint4*>(obase + static_cast<int64_t>(r) * d + half * 32);
-            const uint4* dp = reinterpret_cast<const uint4*>(dobase + static_cast<int64_t>(r) * d + half * 32);
+        const uint4* op = reinterpret_cast<const uint4*>(Ps + r * LDS + half * 32);
+        const uint4* dp = reinterpret_cast<const uint4*>(dOs + r * LDS + half * 32);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint4 a = op[c], bb = dp[c];
-                float2 x, y;
-                x = unpack_bf16x2(a.x); y = unpack_bf16x2(bb.x); acc += x.x * y.x + x.y * y.y;
-                x = unpack_bf16x2(a.y); y = unpack_bf16x2(bb.y); acc += x.x * y.x + x.y * y.y;
-                x = unpack_bf16x2(a.z); y = unpack_bf16x2(bb.z); acc += x.x * y.x + x.y * y.y;
-                x = unpack_bf16x2(a.w); y = unpack_bf16x2(bb.w); acc += x.x * y.x + x.y * y.y;
-            }
+        for (int c = 0; c < 4; ++c) {
+            const uint4 a = op[c], bb = dp[c];
+            float2 x, y;
+            x = unpack_bf16x2(a.x); y = unpack_bf16x2(bb.x); acc += x.x * y.x + x.y * y.y;
+            x = unpack_bf16x2(a.y); y = unpack_bf16x2(bb.y); acc += x.x * y.x + x.y * y.y;
+            x = unpack_bf16x2(a.z); y = unpack_bf16x2(bb.z); acc += x.x * y.x + x.y * y.y;
+            x = unpack_bf16x2(a.w); y = unpack_bf16x2(bb.w); acc += x.x * y.x + x.y * y.y;
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         if (half == 0) {
