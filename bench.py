@@ -244,7 +244,9 @@ def main():
     achieved = gemm_tf / (gemm_ms * 1e-3)
     step_tflops = GFLOP_PER_SAMPLE_C2 * B / 1e3 / (ms_step * 1e-3)
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM, all GEMMs of the step)", "achieved": achieved,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                "traffic": 0.128, "traffic_note": "GB of DRAM read+write per launch of the largest-share shape (c_fc 12800x3072x768: "
+                                                  "24.5 MB read + 103.5 MB written, ncu --set full, profiles/README.md); algorithmic 0.182 GB",
                 "peak_source": pk["source"], "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": gemm_tf,
                 "gemm_launches_per_step": nl.value // prof_steps, "gemm_share_of_step": gemm_ms / ms_step,
                 "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / pk["tflops"],

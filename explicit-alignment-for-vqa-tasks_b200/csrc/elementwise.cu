@@ -316,44 +316,58 @@ __global__ void __launch_bounds__(256, (MAXV <= 6) ? 4 : (MAXV <= 10) ? 3 : 2) l
     }
 }
 
-// column reduction over rows: block = 32 column-pairs x 8 row lanes, 256 rows per block
+// column reduction over rows: block = 32 column-octets (256 columns, 16-byte dy loads) x 8 row lanes, 64 rows per block
 __global__ void __launch_bounds__(256) ln_param_grad_kernel(const bf16* __restrict__ dy, int ld_dy, const float* __restrict__ x,
                                                             int ld_x, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int M, int d) {
     pdl_trigger();
     pdl_wait();
-    __shared__ float sg[8][64], sb[8][64];
+    __shared__ float sg[8][256], sb[8][256];
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int c = blockIdx.x * 64 + 2 * tx;
-    const int r0 = blockIdx.y * 256;
-    float g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
+    const int c = blockIdx.x * 256 + 8 * tx;
+    const int r0 = blockIdx.y * 64;
+    float g[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { g[k] = 0.f; b[k] = 0.f; }
     if (c < d) {
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
             const int r = r0 + ty + 8 * i;
             if (r < M) {
-                const float2 dv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + static_cast<size_t>(r) * ld_dy + c));
-                const float2 xv = *reinterpret_cast<const float2*>(x + static_cast<size_t>(r) * ld_x + c);
+                const uint4 u = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * ld_dy + c);
+                const float4 x0 = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ld_x + c);
+                const float4 x1 = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ld_x + c + 4);
                 const float mu = mean[r], rs = rstd[r];
-                g0 += dv.x * (xv.x - mu) * rs;
-                g1 += dv.y * (xv.y - mu) * rs;
-                b0 += dv.x;
-                b1 += dv.y;
+                float dv[8];
+                float2 t;
+                t = unpack_bf16x2(u.x); dv[0] = t.x; dv[1] = t.y;
+                t = unpack_bf16x2(u.y); dv[2] = t.x; dv[3] = t.y;
+                t = unpack_bf16x2(u.z); dv[4] = t.x; dv[5] = t.y;
+                t = unpack_bf16x2(u.w); dv[6] = t.x; dv[7] = t.y;
+                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    g[k] += dv[k] * (xv[k] - mu) * rs;
+                    b[k] += dv[k];
+                }
             }
         }
     }
-    sg[ty][2 * tx] = g0; sg[ty][2 * tx + 1] = g1;
-    sb[ty][2 * tx] = b0; sb[ty][2 * tx + 1] = b1;
-    __syncthreads();
-    if (ty == 0 && c < d) {
 #pragma unroll
-        for (int i = 1; i < 8; ++i) {
-            g0 += sg[i][2 * tx]; g1 += sg[i][2 * tx + 1];
-            b0 += sb[i][2 * tx]; b1 += sb[i][2 * tx + 1];
-        }
-        atomicAdd(dgamma + c, g0); atomicAdd(dgamma + c + 1, g1);
-        atomicAdd(dbeta + c, b0); atomicAdd(dbeta + c + 1, b1);
+    for (int k = 0; k < 8; ++k) {
+        sg[ty][8 * tx + k] = g[k];
+        sb[ty][8 * tx + k] = b[k];
+    }
+    __syncthreads();
+    const int t = ty * 32 + tx;      // 256 threads: one column each
+    const int col = blockIdx.x * 256 + t;
+    if (col < d) {
+        float gs = 0.f, bs = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { gs += sg[i][t]; bs += sb[i][t]; }
+        atomicAdd(dgamma + col, gs);
+        atomicAdd(dbeta + col, bs);
     }
 }
 
@@ -775,8 +789,8 @@ void layernorm_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, const in
 
 void layernorm_param_grads(const bf16* dy, int ld_dy, const float* x, int ld_x, const float* mean, const float* rstd,
                            float* dgamma, float* dbeta, int M, int d, cudaStream_t s) {
-    EAVQA_CHECK(d % 2 == 0 && ld_dy % 2 == 0 && ld_x % 2 == 0, "layernorm_param_grads alignment");
-    dim3 grid(ceil_div(d, 64), ceil_div(M, 256)), block(32, 8);
+    EAVQA_CHECK(d % 8 == 0 && ld_dy % 8 == 0 && ld_x % 4 == 0, "layernorm_param_grads alignment");
+    dim3 grid(ceil_div(d, 256), ceil_div(M, 64)), block(32, 8);
     launch_kernel(ln_param_grad_kernel, dim3(grid), dim3(block), 0, s, dy, ld_dy, x, ld_x, mean, rstd, dgamma, dbeta, M, d);
     KERNEL_CHECK();
     count_launch();

@@ -918,9 +918,10 @@ void gemm_pick_config(int M, int N, int K, int forced_bn, int forced_cluster, in
     const int kb = ceil_div(K, BK);
     int cluster = forced_cluster;
     if (cluster == 0) {
-        const bool many_tiles = static_cast<int64_t>(num_m) * ceil_div(N, 256) >= 4 * sms;
-        const bool long_k = M >= 8192 && K >= 2048;
-        cluster = (many_tiles || long_k) ? 8 : 1;
+        // In isolation the pair also wins on the K = 768 shapes (+5..25 %), but inside the step those are bound by
+        // their epilogues (CE statistics, gelu + second output, residual) and the coupled pair loses 5-15 %
+        // (profiles/r01_gemm_shapes_v5_pair_everywhere.txt): use it where the main loop dominates.
+        cluster = (K >= 4096 && M >= 2048 && N >= 256) ? 8 : 1;
     }
     EAVQA_CHECK(cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8, "cluster must be 0, 1, 2, 4 or 8");
     int bn = forced_bn;
