@@ -108,9 +108,74 @@ __device__ __forceinline__ float gelu_new_grad(float x) {
     return __fmaf_rn(hx * sech2, du, __fmaf_rn(0.5f, t, 0.5f));
 }
 
+// ---------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): one instruction per TWO floats.  The GEMM epilogues are bound by
+// the instruction stream of their 8 warps (round-1 ncu: ~620 warp-instructions per 32-column chunk, 6.4 clk each), so
+// the element-wise math runs on register pairs.  pk / upk are register renames, not instructions.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 pk1(float x) { return pk(x, x); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 tanh2(f32x2 x) {
+    float a, b;
+    upk(x, a, b);
+    return pk(fast_tanh(a), fast_tanh(b));
+}
+// gelu_new on a pair: 3 FMUL2 + 2 FFMA2 + 2 MUFU
+__device__ __forceinline__ f32x2 gelu_new2(f32x2 x) {
+    const f32x2 c = pk1(0.7978845608028654f), c3 = pk1(0.7978845608028654f * 0.044715f), half = pk1(0.5f);
+    const f32x2 x2 = mul2(x, x);
+    const f32x2 t = tanh2(mul2(x, fma2(x2, c3, c)));
+    const f32x2 hx = mul2(x, half);
+    return fma2(hx, t, hx);
+}
+// d/dx gelu_new on a pair: 4 FMUL2 + 5 FFMA2 + 2 MUFU (signs folded into constants: q = t^2 - 1, ndu = -du/dx)
+__device__ __forceinline__ f32x2 gelu_new_grad2(f32x2 x) {
+    const float cc = 0.7978845608028654f, cc3 = 0.7978845608028654f * 0.044715f;
+    const f32x2 c = pk1(cc), c3 = pk1(cc3), n3c3 = pk1(-3.0f * cc3), nc = pk1(-cc), half = pk1(0.5f), m1 = pk1(-1.0f);
+    const f32x2 x2 = mul2(x, x);
+    const f32x2 t = tanh2(mul2(x, fma2(x2, c3, c)));
+    const f32x2 ndu = fma2(x2, n3c3, nc);
+    const f32x2 q = fma2(t, t, m1);
+    const f32x2 hx = mul2(x, half);
+    return fma2(mul2(hx, q), ndu, fma2(half, t, half));
+}
+// two bf16 packed in a 32-bit word -> a float pair (bf16 -> fp32 is a 16-bit shift)
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t u) { return pk(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(f32x2 v) {
+    float lo, hi;
+    upk(v, lo, hi);
+    return pack_bf16x2(lo, hi);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);

@@ -5,6 +5,8 @@
 // Every matmul on the CLIP-prefix LM path is expressed in this one form by keeping, for each
 // weight, the copy whose contraction dimension is contiguous (frozen LM weights are packed once
 // in both orientations; the trainable mapper's are re-packed each step by pack_weight_kernel).
+// The epilogue combinations the kernels are compiled for are listed in gemm_kernel.cuh (EpiMode);
+// any other combination of the fields below is rejected with an error.
 #pragma once
 #include <string>
 
@@ -51,13 +53,12 @@ struct GemmArgs {
     // MN-major UMMA operands -- no transposed copies.  A / B then point at At / Bt and lda / ldb are their row strides.
     int mn_major = 0;
     int block_n = 0;                 // 0 = pick by wave-quantisation heuristic; else 64/128/192/256
-    int cluster = 0;                 // 0 = heuristic; 1 = single CTAs; 8 = CTA pair (cta_group::2); 2 / 4 = multicast clusters
+    int cluster = 0;                 // 0 = heuristic; 1 = single CTAs; 8 = CTA pair (tcgen05 cta_group::2, 256 x BN tiles)
     GemmEpilogue ep;
 };
 
 // Number of N tiles the heuristic (or block_n) will use: callers size ce_partial with it.
 int gemm_pick_block_n(int M, int N, int K, int forced);
-int gemm_pick_cluster(int M, int N, int bn, int forced);
 // tile width + CTA mode (1 = single CTAs, 8 = CTA pair / cta_group::2) the launcher will use for this problem
 void gemm_pick_config(int M, int N, int K, int forced_bn, int forced_cluster, int* bn_out, int* cluster_out);
 void gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream);
