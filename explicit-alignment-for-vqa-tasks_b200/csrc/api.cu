@@ -107,11 +107,36 @@ int eavqa_train_step(eavqa_handle* h, int32_t batch, int32_t text_len, const flo
 int eavqa_generate(eavqa_handle* h, int32_t batch, int32_t text_len, int32_t n_images, const float* clip,
                    const int64_t* tokens, const int64_t* mask, int64_t sentinel_lo, int64_t sentinel_hi,
                    const float* params, int32_t max_new, int32_t has_eos, int64_t pad_id, int64_t eos_id,
-                   int64_t* tokens_out, float* top_logit, int32_t* steps_out, void* stream) {
+                   int64_t* tokens_out, float* top_logit, float* token_logprob, int32_t* steps_out, void* stream) {
     API_BEGIN
     EAVQA_CHECK(h != nullptr, "null handle");
     h->engine->generate(batch, text_len, n_images, clip, tokens, mask, sentinel_lo, sentinel_hi, params, max_new, has_eos,
-                        pad_id, eos_id, tokens_out, top_logit, steps_out, S(stream));
+                        pad_id, eos_id, tokens_out, top_logit, token_logprob, steps_out, S(stream));
+    API_END
+}
+
+int eavqa_build_caption_labels(const int64_t* tokens, int32_t batch, int32_t text_len, int64_t pad_id, int64_t bos_id,
+                               int64_t* labels, void* stream) {
+    API_BEGIN
+    EAVQA_CHECK(tokens && labels && batch > 0 && text_len > 0, "bad argument");
+    caption_labels(tokens, batch, text_len, pad_id, bos_id, labels, S(stream));
+    API_END
+}
+
+int eavqa_ensemble_select(const float* logprob, const int64_t* tokens, int32_t n_ensembles, int32_t batch, int32_t steps,
+                          const int64_t* skip_ids, int32_t n_skip, float* scores, int32_t* best, int64_t* best_tokens,
+                          void* stream) {
+    API_BEGIN
+    EAVQA_CHECK(logprob && tokens && best && best_tokens && n_ensembles > 0 && batch > 0 && steps > 0, "bad argument");
+    EAVQA_CHECK(n_skip == 0 || skip_ids != nullptr, "skip_ids is null");
+    ensemble_select(logprob, tokens, n_ensembles, batch, steps, skip_ids, n_skip, scores, best, best_tokens, S(stream));
+    API_END
+}
+
+int eavqa_scale_grads(float* grads, int64_t n, const float* scale, void* stream) {
+    API_BEGIN
+    EAVQA_CHECK(grads && scale && n > 0, "bad argument");
+    scale_by_device_scalar(grads, n, scale, S(stream));
     API_END
 }
 

@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
                                                           int64_t* __restrict__ tokens_out,
                                                           int* __restrict__ n_unfinished,
                                                           float* __restrict__ top_logit,
+                                                          float* __restrict__ token_logprob,
                                                           const float* __restrict__ wte,
                                                           const float* __restrict__ wpe_row, int d,
                                                           float* __restrict__ x_next, int* __restrict__ valid_next,
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
     __shared__ float s_val[8];
     __shared__ int s_idx[8];
     __shared__ int s_next;
+    __shared__ float s_best;
     const int b = blockIdx.x;
     const float* lp = logits + static_cast<size_t>(b) * ld;
     float best = -INFINITY;
@@ -643,6 +645,7 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
         if (top_logit) top_logit[static_cast<size_t>(b) * max_new + step] = best;
         if (valid_next) valid_next[static_cast<size_t>(b) * valid_stride] = 1;   // appended position attends as 1
         s_next = best_i;                                            // the RAW argmax is fed back (clipcap.py:423)
+        s_best = best;
     }
     __syncthreads();
     const float4* e = reinterpret_cast<const float4*>(wte + static_cast<size_t>(s_next) * d);
@@ -653,6 +656,102 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
         const float4 w = __ldg(pe + c);
         v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
         o[c] = v;
+    }
+    if (token_logprob != nullptr) {
+        // log softmax(logits)[argmax] = -log sum_v exp(z_v - z_max): second pass over the row (L2-resident), only for
+        // ensemble scoring (few_shot_vqa_executor.py:316, torch.log(softmax(scores)))
+        const float mx = s_best;
+        float sum = 0.f;
+        for (int v = threadIdx.x; v < vocab; v += blockDim.x) sum += __expf(lp[v] - mx);
+        sum = warp_sum(sum);
+        __syncthreads();                       // s_val is reused
+        if (lane == 0) s_val[warp] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < 8; ++i) t += s_val[i];
+            token_logprob[static_cast<size_t>(b) * max_new + step] = -logf(t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ executor-side steps
+// ClipCapExecutor.training_step label construction (clipcap_exector.py:134-150), one thread per caption:
+//   labels = input_ids with pads -> -100; everything up to and including each <BOS> -> -100; tokens after the first
+//   <BOS> are kept; the FIRST pad position gets the pad (= eos) id back as its target and ends the scan.
+__global__ void caption_labels_kernel(const int64_t* __restrict__ tokens, int B, int T, int64_t pad_id, int64_t bos_id,
+                                      int64_t* __restrict__ labels) {
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int64_t* t = tokens + static_cast<size_t>(b) * T;
+    int64_t* l = labels + static_cast<size_t>(b) * T;
+    bool answer = false, ended = false;
+    for (int j = 0; j < T; ++j) {
+        const int64_t tok = t[j];
+        int64_t out;
+        if (ended) {
+            out = (tok == pad_id) ? -100 : tok;            // positions after the break keep the first assignment
+        } else if (tok == pad_id) {                        // first pad (already -100 in the clone): target = pad id, stop
+            out = pad_id;
+            ended = true;
+        } else if (tok == bos_id) {
+            answer = true;
+            out = -100;
+        } else {
+            out = answer ? tok : -100;
+        }
+        l[j] = out;
+    }
+}
+
+// FewShotVQAExecutor.generate_from_ensembles scoring (few_shot_vqa_executor.py:316-331): per row b and ensemble member e,
+// score = sum over generated tokens not in `skip` of their log-probability; best[b] = first argmax over e; the winning
+// member's tokens are copied out.  One warp per row.
+__global__ void ensemble_select_kernel(const float* __restrict__ logprob, const int64_t* __restrict__ tokens, int E, int B, int S,
+                                       const int64_t* __restrict__ skip, int n_skip, float* __restrict__ scores,
+                                       int* __restrict__ best, int64_t* __restrict__ best_tokens) {
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float best_v = -INFINITY;
+    int best_e = 0;
+    for (int e = 0; e < E; ++e) {
+        const size_t base = (static_cast<size_t>(e) * B + b) * S;
+        float acc = 0.f;
+        for (int k = lane; k < S; k += 32) {
+            const int64_t tok = tokens[base + k];
+            bool skipped = false;
+            for (int i = 0; i < n_skip; ++i) skipped |= (tok == skip[i]);
+            if (!skipped) acc += logprob[base + k];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0 && scores != nullptr) scores[static_cast<size_t>(b) * E + e] = acc;
+        if (acc > best_v) {                                // strict: np.argmax keeps the first maximum
+            best_v = acc;
+            best_e = e;
+        }
+    }
+    if (lane == 0) best[b] = best_e;
+    const size_t src = (static_cast<size_t>(best_e) * B + b) * S;
+    for (int k = lane; k < S; k += 32) best_tokens[static_cast<size_t>(b) * S + k] = tokens[src + k];
+}
+
+// x *= *scale unless *scale == 1 (the upstream gradient of loss.backward() is a device scalar that is almost always 1:
+// skipping the pass saves a read + write of the 167 MB gradient buffer per step without a host sync)
+__global__ void __launch_bounds__(256) scale_by_device_scalar_kernel(float4* __restrict__ x, int64_t n4, const float* __restrict__ scale) {
+    pdl_trigger();
+    pdl_wait();
+    const float sc = __ldg(scale);
+    if (sc == 1.0f) return;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 v = x[i];
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        x[i] = v;
     }
 }
 
@@ -849,11 +948,33 @@ void ce_dlogits(bf16* z, int ld, int M, int vocab, int n_cols, const float* lse,
 }
 
 void greedy_step(const float* logits, int ld, int B, int vocab, int step, int max_new, int has_eos, int64_t pad_id,
-                 int64_t eos_id, int* unfinished, int64_t* tokens_out, int* n_unfinished, float* top_logit,
+                 int64_t eos_id, int* unfinished, int64_t* tokens_out, int* n_unfinished, float* top_logit, float* token_logprob,
                  const float* wte, const float* wpe_row, int d, float* x_next, int* valid_next, int valid_stride,
                  cudaStream_t s) {
     launch_kernel(greedy_step_kernel, dim3(B), dim3(256), 0, s, logits, ld, vocab, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out,
-                                         n_unfinished, top_logit, wte, wpe_row, d, x_next, valid_next, valid_stride);
+                                         n_unfinished, top_logit, token_logprob, wte, wpe_row, d, x_next, valid_next, valid_stride);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void caption_labels(const int64_t* tokens, int B, int T, int64_t pad_id, int64_t bos_id, int64_t* labels, cudaStream_t s) {
+    launch_kernel(caption_labels_kernel, dim3(ceil_div(B, 128)), dim3(128), 0, s, tokens, B, T, pad_id, bos_id, labels);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void ensemble_select(const float* logprob, const int64_t* tokens, int E, int B, int S, const int64_t* skip, int n_skip,
+                     float* scores, int* best, int64_t* best_tokens, cudaStream_t s) {
+    launch_kernel(ensemble_select_kernel, dim3(ceil_div(B, 4)), dim3(128), 0, s, logprob, tokens, E, B, S, skip, n_skip, scores, best,
+                  best_tokens);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void scale_by_device_scalar(float* x, int64_t n, const float* scale, cudaStream_t s) {
+    EAVQA_CHECK(n % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "scale_by_device_scalar: 16-byte aligned buffer, n % 4 == 0");
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(n / 4, 256), static_cast<int64_t>(num_sms()) * 8));
+    launch_kernel(scale_by_device_scalar_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<float4*>(x), n / 4, scale);
     KERNEL_CHECK();
     count_launch();
 }

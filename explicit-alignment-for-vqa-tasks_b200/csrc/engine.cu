@@ -624,7 +624,8 @@ void Engine::train_step(int B, int Tt, const float* clip, const int64_t* tokens,
 // ============================================================================================ generation
 void Engine::generate(int B, int Tt, int n_images, const float* clip, const int64_t* tokens, const int64_t* mask,
                       int64_t sent_lo, int64_t sent_hi, const float* params, int max_new, int has_eos, int64_t pad_id,
-                      int64_t eos_id, int64_t* tokens_out, float* top_logit, int32_t* steps_out, cudaStream_t s) {
+                      int64_t eos_id, int64_t* tokens_out, float* top_logit, float* token_logprob, int32_t* steps_out,
+                      cudaStream_t s) {
     EAVQA_CHECK(finalized_, "LM weights not loaded (call eavqa_finalize_lm)");
     EAVQA_CHECK(B > 0 && Tt > 0 && max_new > 0, "empty batch / max_length");
     EAVQA_CHECK(clip && tokens && params && tokens_out && steps_out, "null argument");
@@ -714,7 +715,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         layernorm_fwd(hidden, d, rows, lnf_g_, lnf_b_, hc, d, nullptr, nullptr, B, d, 1e-5f, s);
         gemm(hc, d, wte_bf16_, d, B, Vpad_, d, ep_f32(logits, Vpad_), s);
         greedy_step(logits, Vpad_, B, V_, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out, n_unfinished,
-                    top_logit, wte_f32_, wpe_f32_ + static_cast<size_t>(std::min(T0 + step, cfg_.n_positions - 1)) * d, d, x_a,
+                    top_logit, token_logprob, wte_f32_, wpe_f32_ + static_cast<size_t>(std::min(T0 + step, cfg_.n_positions - 1)) * d, d, x_a,
                     validD + T0 + step, Tmax, s);
     };
     head_and_pick(ha, row_index, 0);

@@ -59,7 +59,7 @@ public:
                     const float* params, float* grads, float* loss_out, cudaStream_t s);
     void generate(int B, int Tt, int n_images, const float* clip, const int64_t* tokens, const int64_t* mask,
                   int64_t sent_lo, int64_t sent_hi, const float* params, int max_new, int has_eos, int64_t pad_id,
-                  int64_t eos_id, int64_t* tokens_out, float* top_logit, int32_t* steps_out, cudaStream_t s);
+                  int64_t eos_id, int64_t* tokens_out, float* top_logit, float* token_logprob, int32_t* steps_out, cudaStream_t s);
 
 private:
     struct MapperFwd;   // activations of one mapper forward (arena-backed)

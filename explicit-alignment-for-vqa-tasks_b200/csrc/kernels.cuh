@@ -63,8 +63,18 @@ void ce_dlogits(bf16* z, int ld, int M, int vocab, int n_cols, const float* lse,
 // tokens_out[b, step] = out; x_next[b] = wte[nxt] + wpe[pos]; n_unfinished[step] = sum(unfinished)
 void greedy_step(const float* logits, int ld, int B, int vocab, int step, int max_new, int has_eos, int64_t pad_id,
                  int64_t eos_id, int* unfinished, int64_t* tokens_out, int* n_unfinished, float* top_logit,
-                 const float* wte, const float* wpe_row, int d, float* x_next, int* valid_next, int valid_stride,
+                 float* token_logprob /* optional: log softmax of the picked token */, const float* wte, const float* wpe_row, int d, float* x_next, int* valid_next, int valid_stride,
                  cudaStream_t s);
+
+// ---------------------------------------------------------------- executor-side steps (elementwise.cu)
+// ClipCapExecutor.training_step label construction (clipcap_exector.py:134-150): labels [B, T] int64
+void caption_labels(const int64_t* tokens, int B, int T, int64_t pad_id, int64_t bos_id, int64_t* labels, cudaStream_t s);
+// FewShotVQAExecutor.generate_from_ensembles (few_shot_vqa_executor.py:316-331): logprob / tokens [E, B, S];
+// scores [B, E] (optional), best [B], best_tokens [B, S]
+void ensemble_select(const float* logprob, const int64_t* tokens, int E, int B, int S, const int64_t* skip, int n_skip,
+                     float* scores, int* best, int64_t* best_tokens, cudaStream_t s);
+// x[0..n) *= *scale (device scalar); no memory traffic when *scale == 1
+void scale_by_device_scalar(float* x, int64_t n, const float* scale, cudaStream_t s);
 
 // ---------------------------------------------------------------- optimiser (elementwise.cu)
 // torch.optim.AdamW semantics on the flat mapper buffer (clipcap_exector.py:79-81): decoupled weight decay,

@@ -40,8 +40,12 @@ PROTOTYPES = {
     "eavqa_train_step": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "eavqa_generate": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
-                                 c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p, C.POINTER(c_int32),
+                                 c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_void_p, C.POINTER(c_int32),
                                  c_void_p]),
+    "eavqa_build_caption_labels": (C.c_int, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
+    "eavqa_ensemble_select": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    "eavqa_scale_grads": (C.c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "eavqa_splice": (C.c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_int64,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "eavqa_launch_count": (c_int64, []),

@@ -106,7 +106,12 @@ class _TrainStepFn(torch.autograd.Function):
         ctx.grads = None
         if grads is None:
             return (None,) * (6 + len(model._param_list))
-        grads.mul_(g)
+        # grads *= g on the device; the kernel returns at once when g == 1 (plain loss.backward()): no host sync, and no
+        # extra pass over the 167 MB buffer
+        with torch.cuda.device(grads.device):
+            _lib.check(_lib.load().eavqa_scale_grads(grads.data_ptr(), grads.numel(),
+                                                     g.to(device=grads.device, dtype=torch.float32).contiguous().data_ptr(),
+                                                     _lib.current_stream()))
         model.last_flat_grads = grads
         outs = [grads[o:o + n].view(shape) for (o, n, shape) in model._slices]
         return (None, None, None, None, None, None, *outs)
@@ -321,10 +326,14 @@ class ClipCaptionModelB200(nn.Module):
     @torch.no_grad()
     def generate(self, question_tokens: torch.Tensor, prefix: torch.Tensor, question_mask: Optional[torch.Tensor] = None,
                  max_length: Optional[int] = 10, pad_token_id: Optional[int] = None, eos_token_id: Optional[int] = None,
-                 special_token_id: Optional[int] = None, return_top_logits: bool = False, **unused):
+                 special_token_id: Optional[int] = None, return_top_logits: bool = False, return_logprobs: bool = False,
+                 **unused):
         """clipcap.py:344-471 (prepend; returns ``list[list[int]]``) and, when ``prefix`` is ``[B, k+1, 1, D]`` and a
         sentinel id is known, the k-shot assembly of vct0.py:446-464,494-533 (returns a ``LongTensor [B, steps]`` like
-        ``lm.generate``).  Extra few-shot kwargs of ``FewShotVQAExecutor`` (``decoder_input_ids=None`` ...) are accepted."""
+        ``lm.generate``).  Extra few-shot kwargs of ``FewShotVQAExecutor`` (``decoder_input_ids=None`` ...) are accepted.
+        ``return_logprobs=True`` returns ``(tokens [B, steps] LongTensor, logprob [B, steps])`` on the device: the
+        log-softmax of every picked token, i.e. what ``generate_from_ensembles`` gathers from ``outputs.scores``
+        (few_shot_vqa_executor.py:316-323)."""
         self._ensure_engine()
         L = _lib.load()
         tokens = self._prep(question_tokens, torch.int64)
@@ -347,13 +356,16 @@ class ClipCaptionModelB200(nn.Module):
         dev = self._flat.device
         out = torch.empty(B, max_length, dtype=torch.int64, device=dev)
         top = torch.empty(B, max_length, dtype=torch.float32, device=dev) if return_top_logits else None
+        lp = torch.empty(B, max_length, dtype=torch.float32, device=dev) if return_logprobs else None
         steps = C.c_int32(0)
         with torch.cuda.device(dev):
             _lib.check(L.eavqa_generate(self._handle, B, Tt, n_img, clip.data_ptr(), tokens.data_ptr(), _lib.ptr(mask), lo, hi,
                                         self._flat.data_ptr(), max_length, 1 if eos is not None else 0,
                                         pad if pad is not None else 0, eos if eos is not None else 0, out.data_ptr(),
-                                        _lib.ptr(top), C.byref(steps), _lib.current_stream()))
+                                        _lib.ptr(top), _lib.ptr(lp), C.byref(steps), _lib.current_stream()))
         out = out[:, :steps.value]
+        if return_logprobs:
+            return out, lp[:, :steps.value]
         if return_top_logits:
             return out.cpu().tolist(), top[:, :steps.value].cpu()
         if few_shot:

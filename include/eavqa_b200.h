@@ -87,12 +87,14 @@ int eavqa_train_step(eavqa_handle* h, int32_t batch, int32_t text_len, const flo
  *                  next image's P prefix rows; every row must hold exactly n_images sentinels.
  *   tokens_out [B, max_new] int64 (device); has_eos = 0 reproduces eos_token_id=None.
  *   top_logit  [B, max_new] fp32 (device) or NULL: the winning logit of every step (diagnostics).
+ *   token_logprob [B, max_new] fp32 (device) or NULL: log softmax(logits)[picked token] of every step -- what
+ *              FewShotVQAExecutor.generate_from_ensembles reads out of `outputs.scores` (few_shot_vqa_executor.py:316-323).
  *   steps_out  (host int32): number of decode steps executed before every row had finished (clipcap.py:463);
  *              only tokens_out[:, :steps_out] is meaningful. */
 int eavqa_generate(eavqa_handle* h, int32_t batch, int32_t text_len, int32_t n_images, const float* clip,
                    const int64_t* tokens, const int64_t* mask, int64_t sentinel_lo, int64_t sentinel_hi,
                    const float* params, int32_t max_new, int32_t has_eos, int64_t pad_id, int64_t eos_id,
-                   int64_t* tokens_out, float* top_logit, int32_t* steps_out, void* stream);
+                   int64_t* tokens_out, float* top_logit, float* token_logprob, int32_t* steps_out, void* stream);
 
 /* VCT0Model.insert_prefix_into_input (vct0.py:494-533) on caller-supplied embeddings (golden-vector parity).
  *   text_table [vocab, d] fp32 rows looked up by token id; prefix [B, n_images*P, d] fp32
@@ -103,6 +105,26 @@ int eavqa_splice(int32_t batch, int32_t text_len, int32_t n_images, int32_t pref
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t eavqa_launch_count(void);
+
+/* ---- the steps right around the path inside the reference's executors ---- */
+/* ClipCapExecutor.training_step label construction (clipcap_exector.py:134-150), replacing its Python double loop over
+ * [B, T] tensor elements: labels = input_ids with pads -> -100, everything up to and including <BOS> -> -100, and the
+ * FIRST pad position set back to pad_id (the EOS target).  tokens / labels [B, text_len] int64 on the device. */
+int eavqa_build_caption_labels(const int64_t* tokens, int32_t batch, int32_t text_len, int64_t pad_id, int64_t bos_id,
+                               int64_t* labels, void* stream);
+
+/* FewShotVQAExecutor.generate_from_ensembles (few_shot_vqa_executor.py:293-332): logprob / tokens [n_ensembles, B, steps]
+ * (token_logprob / tokens_out of `eavqa_generate`, one call per ensemble member); a row's sequence score is the sum of
+ * the log-probabilities of its tokens not listed in skip_ids (the reference skips ids 0, 1, 2 = T5 pad / eos / unk);
+ * best[b] = first argmax over members (np.argmax), best_tokens [B, steps] = the winning member's tokens;
+ * scores [B, n_ensembles] fp32 or NULL. */
+int eavqa_ensemble_select(const float* logprob, const int64_t* tokens, int32_t n_ensembles, int32_t batch, int32_t steps,
+                          const int64_t* skip_ids, int32_t n_skip, float* scores, int32_t* best, int64_t* best_tokens,
+                          void* stream);
+
+/* grads[0..n) *= *scale (device fp32 scalar: the upstream gradient autograd hands to backward()); skips the pass when
+ * *scale == 1 without a host sync.  n % 4 == 0. */
+int eavqa_scale_grads(float* grads, int64_t n, const float* scale, void* stream);
 
 /* torch.optim.AdamW (clipcap_exector.py:79-81) on the flat mapper buffer, one fused pass:
  * params/grads/exp_avg/exp_avg_sq [n] fp32 on the device; `step` counts from 1; g = grads * grad_scale

@@ -200,7 +200,8 @@ def train_step(lm: Dict[str, Tensor], mapper: Dict[str, Tensor], cfg: dict, ques
 @torch.no_grad()
 def generate_from_embeddings(lm: Dict[str, Tensor], cfg: dict, embedding_cat: Tensor, attention_mask: Tensor,
                              max_length: int = 10, pad_token_id: Optional[int] = None,
-                             eos_token_id: Optional[int] = None, return_margins: bool = False):
+                             eos_token_id: Optional[int] = None, return_margins: bool = False,
+                             return_logprobs: bool = False):
     """``ClipCaptionModel._generate_from_embeddings`` (``clipcap.py:387-471``).
 
     No KV cache: the whole sequence is re-run each step (``:416-419``); the next
@@ -219,6 +220,7 @@ def generate_from_embeddings(lm: Dict[str, Tensor], cfg: dict, embedding_cat: Te
     attention_mask = attention_mask.float()
     tokens = None
     margins = []
+    logprobs = []          # log softmax(last)[argmax]: what few_shot_vqa_executor.py:316-323 reads from outputs.scores
     emb = embedding_cat
     for _ in range(max_length):
         hidden = gpt2_hidden(lm, emb, attention_mask, cfg["n_layer"], cfg["n_head"])
@@ -227,6 +229,8 @@ def generate_from_embeddings(lm: Dict[str, Tensor], cfg: dict, embedding_cat: Te
         if return_margins:
             top2 = last.topk(2, dim=-1).values
             margins.append((top2[:, 0] - top2[:, 1]).clone())
+        if return_logprobs:
+            logprobs.append(torch.log_softmax(last.double(), dim=-1).gather(1, nxt).squeeze(1).float())
         nxt_embed = lm["transformer.wte.weight"][nxt]
         out = nxt
         if eos_token_id is not None:
@@ -239,6 +243,8 @@ def generate_from_embeddings(lm: Dict[str, Tensor], cfg: dict, embedding_cat: Te
         if unfinished.max() == 0:
             break
     token_list = tokens.cpu().numpy().astype(int).tolist()
+    if return_logprobs:
+        return token_list, torch.stack(margins, dim=1) if return_margins else None, torch.stack(logprobs, dim=1)
     if return_margins:
         return token_list, torch.stack(margins, dim=1)
     return token_list
