@@ -243,10 +243,24 @@ def main():
     gemm_ms, gemm_tf = tot_ms.value / prof_steps, tot_fl.value / prof_steps / 1e12
     achieved = gemm_tf / (gemm_ms * 1e-3)
     step_tflops = GFLOP_PER_SAMPLE_C2 * B / 1e3 / (ms_step * 1e-3)
+    # DRAM traffic of the GEMM launches: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 196 GEMM launches
+    # of one step, per launch like `achieved` (profiles/r01_gemm_traffic_v13.json, made by tools/ncu_step_summary.py from
+    # the committed launch list); algorithmic bytes per launch from the same per-launch records as the timings.
+    import re
+    alg = [float(m.group(2)) * int(m.group(1)) for m in re.finditer(r"launches=(\d+) .*alg_mbytes=([0-9.]+)", rep.value.decode())]
+    alg_gb_per_launch = sum(alg) / 1e3 / max(nl.value, 1)
+    traffic, traffic_note = None, "no ncu traffic summary under profiles/"
+    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic_v13.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            t = json.load(f)
+        traffic = t["gemm_dram_bytes_per_launch"] / 1e9
+        traffic_note = ("GB of DRAM read+write per GEMM launch, averaged over the %d GEMM launches of one step (ncu, %s); "
+                        "algorithmic %.4f GB per launch (operands + outputs once; part of every output is still in the "
+                        "126 MB L2 when its kernel ends)" % (t["gemm_launches_per_step"], os.path.basename(tp), alg_gb_per_launch))
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM, all GEMMs of the step)", "achieved": achieved,
                 "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                "traffic": 0.128, "traffic_note": "GB of DRAM read+write per launch of the largest-share shape (c_fc 12800x3072x768: "
-                                                  "24.5 MB read + 103.5 MB written, ncu --set full, profiles/README.md); algorithmic 0.182 GB",
+                "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": pk["source"], "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": gemm_tf,
                 "gemm_launches_per_step": nl.value // prof_steps, "gemm_share_of_step": gemm_ms / ms_step,
                 "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / pk["tflops"],

@@ -4,6 +4,7 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "gemm.cuh"
@@ -166,9 +167,38 @@ Engine::Engine(const eavqa_config& cfg) : cfg_(cfg) {
     }
     layers_.resize(L_);
     for (auto& l : layers_) std::memset(&l, 0, sizeof(LmLayer));
+    const char* e = getenv("EAVQA_WGRAD_STREAM");
+    side_enabled_ = !(e != nullptr && e[0] == '0');
+    CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&join_event_, cudaEventDisableTiming));
+}
+
+cudaStream_t Engine::fork(cudaStream_t main) {
+    if (!side_enabled_ || gemm_profile_active()) return main;
+    if (fork_used_ == fork_events_.size()) {
+        cudaEvent_t ev;
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        fork_events_.push_back(ev);
+    }
+    cudaEvent_t ev = fork_events_[fork_used_++];
+    CUDA_CHECK(cudaEventRecord(ev, main));
+    CUDA_CHECK(cudaStreamWaitEvent(side_, ev, 0));
+    return side_;
+}
+
+void Engine::join(cudaStream_t main) {
+    const bool forked = fork_used_ > 0;
+    fork_used_ = 0;
+    if (!forked) return;
+    CUDA_CHECK(cudaEventRecord(join_event_, side_));
+    CUDA_CHECK(cudaStreamWaitEvent(main, join_event_, 0));
 }
 
 Engine::~Engine() {
+    if (side_) cudaStreamSynchronize(side_);
+    for (cudaEvent_t ev : fork_events_) cudaEventDestroy(ev);
+    if (join_event_) cudaEventDestroy(join_event_);
+    if (side_) cudaStreamDestroy(side_);
     for (void* p : owned_) cudaFree(p);
     if (host_flags_) cudaFreeHost(host_flags_);
 }
@@ -405,21 +435,26 @@ void Engine::mapper_backward(const float* params, const MapperW& w, const Mapper
         // dY2 = d loss / d prefix, viewed [N, P*d] (rows of dh with the LM's batch stride); bias grads = column sums
         convert_transpose_f32(dprefix, static_cast<int>(dprefix_batch_stride), N, out, dy2, out, nullptr, 0,
                               grads + pofs("model.2.bias"), s);
-        gemm_wgrad(dy2, out, f.y1, hdim, out, hdim, N, grads + pofs("model.2.weight"), hdim, s);            // dW2 = dY2^T Y1
+        gemm_wgrad(dy2, out, f.y1, hdim, out, hdim, N, grads + pofs("model.2.weight"), hdim, fork(s));       // dW2 = dY2^T Y1
         GemmEpilogue e = ep_bf16(dy1, hdim);
         e.dact = DACT_TANH; e.aux = f.y1; e.ld_aux = hdim;
         gemm(dy2, out, w.m2_t, out, N, hdim, out, e, s);                                                     // dY1 = (dY2 W2) * tanh'
         convert_transpose_bf16(dy1, hdim, N, hdim, nullptr, 0, grads + pofs("model.0.bias"), s);
-        gemm_wgrad(dy1, hdim, f.clip_bf16, D_, hdim, D_, N, grads + pofs("model.0.weight"), D_, s);         // dW1 = dY1^T clip
+        gemm_wgrad(dy1, hdim, f.clip_bf16, D_, hdim, D_, N, grads + pofs("model.0.weight"), D_, fork(s));    // dW1 = dY1^T clip
+        join(s);
         return;
     }
     const int cl = cfg_.clip_length, S = S_, M2 = N * S, n = cfg_.mapper_layers;
     const size_t m2 = static_cast<size_t>(M2);
     float* dx = arena_.get<float>(m2 * d);
-    bf16* dx_b = arena_.get<bf16>(m2 * d);
-    bf16* dm1 = arena_.get<bf16>(m2 * 2 * d);
-    bf16* dsmall = arena_.get<bf16>(m2 * d);                              // dg / d_o / da
-    bf16* dqkv = arena_.get<bf16>(m2 * 3 * d);
+    // operands of the weight-gradient GEMMs get their own buffers per layer (55 MB / layer at N = 256): those GEMMs run
+    // on the side stream and must not race with the main stream reusing a buffer further down the dgrad chain
+    std::vector<bf16*> dx_mlp(n), dx_att(n), dm1(n), dqkv(n);
+    for (int l = 0; l < n; ++l) {
+        dx_mlp[l] = arena_.get<bf16>(m2 * d); dx_att[l] = arena_.get<bf16>(m2 * d);
+        dm1[l] = arena_.get<bf16>(m2 * 2 * d); dqkv[l] = arena_.get<bf16>(m2 * 3 * d);
+    }
+    bf16* dsmall = arena_.get<bf16>(m2 * d);                              // dg / d_o / da (main stream only)
     bf16* dlin = arena_.get<bf16>(static_cast<size_t>(N) * cl * d);
     if (grads == nullptr) return;         // planning pass only
     {
@@ -433,32 +468,33 @@ void Engine::mapper_backward(const float* params, const MapperW& w, const Mapper
     for (int l = n - 1; l >= 0; --l) {
         const std::string p = "transformer.layers." + std::to_string(l) + ".";
         // ---- MLP branch: x2 = x1 + fc2(relu(fc1(LN2(x1))))   (clipcap.py:61-67,116)
-        convert_transpose_f32(dx, d, M2, d, dx_b, d, nullptr, 0, grads + pofs(p + "mlp.fc2.bias"), s);
-        gemm_wgrad(dx_b, d, f.m1[l], 2 * d, d, 2 * d, M2, grads + pofs(p + "mlp.fc2.weight"), 2 * d, s);  // dW2 = dx^T m1
+        convert_transpose_f32(dx, d, M2, d, dx_mlp[l], d, nullptr, 0, grads + pofs(p + "mlp.fc2.bias"), s);
+        gemm_wgrad(dx_mlp[l], d, f.m1[l], 2 * d, d, 2 * d, M2, grads + pofs(p + "mlp.fc2.weight"), 2 * d, fork(s));  // dW2 = dx^T m1
         {
-            GemmEpilogue e = ep_bf16(dm1, 2 * d);
+            GemmEpilogue e = ep_bf16(dm1[l], 2 * d);
             e.dact = DACT_RELU; e.aux = f.m1[l]; e.ld_aux = 2 * d;
-            gemm(dx_b, d, w.w2_t[l], d, M2, 2 * d, d, e, s);                                               // dm1 = (dx W2) * relu'
+            gemm(dx_mlp[l], d, w.w2_t[l], d, M2, 2 * d, d, e, s);                                          // dm1 = (dx W2) * relu'
         }
-        convert_transpose_bf16(dm1, 2 * d, M2, 2 * d, nullptr, 0, grads + pofs(p + "mlp.fc1.bias"), s);
-        gemm_wgrad(dm1, 2 * d, f.g[l], d, 2 * d, d, M2, grads + pofs(p + "mlp.fc1.weight"), d, s);        // dW1 = dm1^T g
-        gemm(dm1, 2 * d, w.w1_t[l], 2 * d, M2, d, 2 * d, ep_bf16(dsmall, d), s);                          // dg = dm1 W1
+        convert_transpose_bf16(dm1[l], 2 * d, M2, 2 * d, nullptr, 0, grads + pofs(p + "mlp.fc1.bias"), s);
+        gemm_wgrad(dm1[l], 2 * d, f.g[l], d, 2 * d, d, M2, grads + pofs(p + "mlp.fc1.weight"), d, fork(s));  // dW1 = dm1^T g
+        gemm(dm1[l], 2 * d, w.w1_t[l], 2 * d, M2, d, 2 * d, ep_bf16(dsmall, d), s);                       // dg = dm1 W1
         layernorm_bwd(dsmall, d, f.x[2 * l + 1], d, nullptr, params + pofs(p + "norm2.weight"), f.mean2[l], f.rstd2[l], dx, d,
                       1, nullptr, 0, grads + pofs(p + "norm2.weight"), grads + pofs(p + "norm2.bias"), M2, d, 1e-5f, s);
         // ---- attention branch: x1 = x0 + project(attn(LN1(x0)))   (clipcap.py:81-104,115)
-        convert_transpose_f32(dx, d, M2, d, dx_b, d, nullptr, 0, grads + pofs(p + "attn.project.bias"), s);
-        gemm_wgrad(dx_b, d, f.o[l], d, d, d, M2, grads + pofs(p + "attn.project.weight"), d, s);          // dWp = dx^T o
-        gemm(dx_b, d, w.wp_t[l], d, M2, d, d, ep_bf16(dsmall, d), s);                                     // d_o = dx Wp
-        mapper_attention_bwd(f.qkv[l], dsmall, dqkv, N, S, 8, d / 8, s);
-        gemm_wgrad(dqkv, 3 * d, f.a[l], d, 3 * d, d, M2, grads + pofs(p + "attn.to_queries.weight"), d, s);   // d[Wq;Wkv] = dqkv^T a
-        gemm(dqkv, 3 * d, w.wqkv_t[l], 3 * d, M2, d, 3 * d, ep_bf16(dsmall, d), s);                       // da = dqkv [Wq;Wkv]
+        convert_transpose_f32(dx, d, M2, d, dx_att[l], d, nullptr, 0, grads + pofs(p + "attn.project.bias"), s);
+        gemm_wgrad(dx_att[l], d, f.o[l], d, d, d, M2, grads + pofs(p + "attn.project.weight"), d, fork(s));   // dWp = dx^T o
+        gemm(dx_att[l], d, w.wp_t[l], d, M2, d, d, ep_bf16(dsmall, d), s);                                 // d_o = dx Wp
+        mapper_attention_bwd(f.qkv[l], dsmall, dqkv[l], N, S, 8, d / 8, s);
+        gemm_wgrad(dqkv[l], 3 * d, f.a[l], d, 3 * d, d, M2, grads + pofs(p + "attn.to_queries.weight"), d, fork(s));   // d[Wq;Wkv] = dqkv^T a
+        gemm(dqkv[l], 3 * d, w.wqkv_t[l], 3 * d, M2, d, 3 * d, ep_bf16(dsmall, d), s);                    // da = dqkv [Wq;Wkv]
         layernorm_bwd(dsmall, d, f.x[2 * l], d, nullptr, params + pofs(p + "norm1.weight"), f.mean1[l], f.rstd1[l], dx, d, 1,
                       nullptr, 0, grads + pofs(p + "norm1.weight"), grads + pofs(p + "norm1.bias"), M2, d, 1e-5f, s);
     }
     // x0 = cat(linear(clip).view(N, cl, d), prefix_const)
     sum_over_batch_f32(dx + static_cast<size_t>(cl) * d, static_cast<int64_t>(S) * d, N, P_ * d, grads + pofs("prefix_const"), s);
     convert_transpose_f32(dx, S * d, N, cl * d, dlin, cl * d, nullptr, 0, grads + pofs("linear.bias"), s);
-    gemm_wgrad(dlin, cl * d, f.clip_bf16, D_, cl * d, D_, N, grads + pofs("linear.weight"), D_, s);        // dWl = dlin^T clip
+    gemm_wgrad(dlin, cl * d, f.clip_bf16, D_, cl * d, D_, N, grads + pofs("linear.weight"), D_, fork(s));  // dWl = dlin^T clip
+    join(s);
 }
 
 // ============================================================================================ LM block

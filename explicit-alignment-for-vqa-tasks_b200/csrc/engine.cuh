@@ -89,6 +89,15 @@ private:
     std::vector<TensorInfo> mapper_tensors_;
     int64_t mapper_count_ = 0;
     Arena arena_;
+    // Weight-gradient GEMMs of the mapper backward run on a side stream: they only feed the gradient buffer, so they
+    // overlap the (sub-wave, latency-bound) dgrad chain on the main stream; forked and joined with events per step.
+    cudaStream_t side_ = nullptr;
+    std::vector<cudaEvent_t> fork_events_;
+    size_t fork_used_ = 0;
+    cudaEvent_t join_event_ = nullptr;
+    bool side_enabled_ = true;           // EAVQA_WGRAD_STREAM=0 serialises everything on the caller's stream (measurements)
+    cudaStream_t fork(cudaStream_t main);   // side stream made to wait for everything enqueued on `main` so far
+    void join(cudaStream_t main);           // `main` waits for the side stream
     int32_t* host_flags_ = nullptr;      // pinned: n_unfinished[max] + err flag read-back
     int host_flags_cap_ = 0;
 };

@@ -67,6 +67,7 @@ int64_t gemm_launch_count();
 // per-launch CUDA-event timing of the GEMM kernel (bench.py's roofline leg): begin() arms it, end() synchronises,
 // returns total kernel milliseconds / FLOPs (2MNK) / launches and a per-shape text report
 void gemm_profile_begin();
+bool gemm_profile_active();      // while armed the engine keeps every kernel on one stream, so launch durations do not overlap
 void gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches, std::string* report);
 
 }  // namespace eavqa

@@ -28,7 +28,7 @@ namespace eavqa {
 // ---- host services implemented in gemm_tcgen05.cu
 enum MapKind { MAP_OPERAND = 0, MAP_EPI_BF16 = 1, MAP_EPI_F32 = 2 };
 CUtensorMap gemm_make_map(const void* ptr, int rows, int cols, int ld, int box_rows, int kind);
-void gemm_prof_before(cudaStream_t stream, int M, int N, int K, int bn_tag, void** token);
+void gemm_prof_before(cudaStream_t stream, const GemmArgs& a, int bn_tag, void** token);
 void gemm_prof_after(cudaStream_t stream, void* token);
 
 // Epilogue modes (what happens to the fp32 accumulator tile before it is stored)
@@ -758,7 +758,7 @@ void launch_1cta(const GemmArgs& a, cudaStream_t stream) {
     const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN) * split;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     void* token = nullptr;
-    gemm_prof_before(stream, a.M, a.N, a.K, BN, &token);
+    gemm_prof_before(stream, a, BN, &token);
     launch_with_attrs(gemm_bf16_tn_kernel<BN, MODE, MN>, grid, C::SMEM, 1, stream, maps, a);
     gemm_prof_after(stream, token);
 }
@@ -779,7 +779,7 @@ void launch_2cta(const GemmArgs& a, cudaStream_t stream) {
     const int max_clusters = num_sms() / 2;
     const int grid = (tiles < max_clusters ? tiles : max_clusters) * 2;
     void* token = nullptr;
-    gemm_prof_before(stream, a.M, a.N, a.K, BN + 1000, &token);
+    gemm_prof_before(stream, a, BN + 1000, &token);
     launch_with_attrs(gemm_bf16_tn_2cta_kernel<BN, MODE>, grid, C::SMEM, 2, stream, maps, a);
     gemm_prof_after(stream, token);
 }

@@ -19,10 +19,12 @@ int64_t gemm_launch_count() { return g_gemm_launches.load(); }
 struct ProfRec {
     cudaEvent_t start, stop;
     int M, N, K, bn;
+    double bytes;      // algorithmic HBM bytes of the launch: operands + outputs (+ residual / aux operand), each once
 };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 
+bool gemm_profile_active() { return g_prof_on; }
 void gemm_profile_begin() {
     g_prof.clear();
     g_prof_on = true;
@@ -31,6 +33,7 @@ void gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches, 
     g_prof_on = false;
     CUDA_CHECK(cudaDeviceSynchronize());
     std::map<std::tuple<int, int, int, int>, std::pair<double, int>> by_shape;
+    std::map<std::tuple<int, int, int, int>, double> bytes_by_shape;
     double ms_sum = 0, fl_sum = 0;
     for (auto& r : g_prof) {
         float ms = 0.f;
@@ -42,6 +45,7 @@ void gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches, 
         auto& e = by_shape[std::make_tuple(r.M, r.N, r.K, r.bn)];
         e.first += ms;
         e.second += 1;
+        bytes_by_shape[std::make_tuple(r.M, r.N, r.K, r.bn)] += r.bytes;
     }
     if (total_ms) *total_ms = ms_sum;
     if (total_flops) *total_flops = fl_sum;
@@ -52,8 +56,9 @@ void gemm_profile_end(double* total_ms, double* total_flops, int64_t* launches, 
             const int M = std::get<0>(kv.first), N = std::get<1>(kv.first), K = std::get<2>(kv.first), bn = std::get<3>(kv.first);
             const double ms = kv.second.first / kv.second.second;
             char line[256];
-            snprintf(line, sizeof(line), "M=%d N=%d K=%d bn=%d launches=%d avg_ms=%.4f tflops=%.1f\n", M, N, K, bn,
-                     kv.second.second, ms, 2.0 * M * N * K / (ms * 1e-3) / 1e12);
+            snprintf(line, sizeof(line), "M=%d N=%d K=%d bn=%d launches=%d avg_ms=%.4f tflops=%.1f alg_mbytes=%.2f\n", M, N, K, bn,
+                     kv.second.second, ms, 2.0 * M * N * K / (ms * 1e-3) / 1e12,
+                     bytes_by_shape[kv.first] / kv.second.second / 1e6);
             *report += line;
         }
     }
@@ -70,13 +75,18 @@ int num_sms() {
     return n;
 }
 
-void gemm_prof_before(cudaStream_t stream, int M, int N, int K, int bn_tag, void** token) {
+void gemm_prof_before(cudaStream_t stream, const GemmArgs& a, int bn_tag, void** token) {
+    const int M = a.M, N = a.N, K = a.K;
     *token = nullptr;
     if (!g_prof_on) return;
     ProfRec* rec = new ProfRec;
     CUDA_CHECK(cudaEventCreate(&rec->start));
     CUDA_CHECK(cudaEventCreate(&rec->stop));
     rec->M = M; rec->N = N; rec->K = K; rec->bn = bn_tag;
+    const double mn = static_cast<double>(M) * N;
+    rec->bytes = 2.0 * M * K + 2.0 * N * K + (a.ep.out ? (a.ep.out_fp32 ? 4.0 : 2.0) * mn : 0.0) + (a.ep.out2 ? 2.0 * mn : 0.0) +
+                 (a.ep.residual ? 4.0 * mn : 0.0) + (a.ep.dact != DACT_NONE ? 2.0 * mn : 0.0) +
+                 (a.ep.split_k > 1 ? 4.0 * mn * (a.ep.split_k - 1) : 0.0);
     CUDA_CHECK(cudaEventRecord(rec->start, stream));
     *token = rec;
 }

@@ -134,7 +134,9 @@ int eavqa_adamw_step(float* params, const float* grads, float* exp_avg, float* e
 
 /* Per-launch CUDA-event timing of the tcgen05 GEMM kernel (the dominant kernel; bench.py's roofline leg).
  * begin() arms it; end() synchronises the device and returns summed kernel milliseconds, FLOPs (2MNK) and
- * launch count since begin(), plus a per-shape text report.  Not for use inside a timed region. */
+ * launch count since begin(), plus a per-shape text report (with the algorithmic HBM bytes per launch).  While armed,
+ * the mapper's weight-gradient GEMMs stay on the caller's stream (normally they overlap the dgrad chain on a side
+ * stream), so that per-launch durations do not overlap.  Not for use inside a timed region. */
 int eavqa_profile_begin(void);
 int eavqa_profile_end(double* total_ms, double* total_flops, int64_t* launches, char* report, size_t report_cap);
 
