@@ -363,24 +363,28 @@ struct Engine::MapperFwd {
 
 void Engine::pack_mapper_weights(const float* params, bool bwd, MapperW& w, cudaStream_t s) {
     const int d = d_;
+    std::vector<PackJob> jobs;
     auto pack = [&](const std::string& name, int rows, int cols, bf16* nat, bf16* tr) {
-        convert_transpose_f32(params + pofs(name), cols, rows, cols, nat, cols, tr, rows, nullptr, s);
+        PackJob j;
+        j.src = params + pofs(name); j.dst = nat; j.dst_t = tr; j.rows = rows; j.cols = cols; j.tile_begin = 0;
+        jobs.push_back(j);
     };
     if (cfg_.mapper_type == EAVQA_MAPPER_MLP) {
         const int hdim = d * P_ / 2;
         pack("model.0.weight", hdim, D_, w.m1, nullptr);
         pack("model.2.weight", d * P_, hdim, w.m2, bwd ? w.m2_t : nullptr);
-        return;
+    } else {
+        for (int i = 0; i < cfg_.mapper_layers; ++i) {
+            const std::string p = "transformer.layers." + std::to_string(i) + ".";
+            // to_queries [d, d] and to_keys_values [2d, d] are adjacent in the flat buffer: one [3d, d] matrix
+            pack(p + "attn.to_queries.weight", 3 * d, d, w.wqkv[i], bwd ? w.wqkv_t[i] : nullptr);
+            pack(p + "attn.project.weight", d, d, w.wp[i], bwd ? w.wp_t[i] : nullptr);
+            pack(p + "mlp.fc1.weight", 2 * d, d, w.w1[i], bwd ? w.w1_t[i] : nullptr);
+            pack(p + "mlp.fc2.weight", d, 2 * d, w.w2[i], bwd ? w.w2_t[i] : nullptr);
+        }
+        pack("linear.weight", cfg_.clip_length * d, D_, w.wl, nullptr);
     }
-    for (int i = 0; i < cfg_.mapper_layers; ++i) {
-        const std::string p = "transformer.layers." + std::to_string(i) + ".";
-        // to_queries [d, d] and to_keys_values [2d, d] are adjacent in the flat buffer: one [3d, d] matrix
-        pack(p + "attn.to_queries.weight", 3 * d, d, w.wqkv[i], bwd ? w.wqkv_t[i] : nullptr);
-        pack(p + "attn.project.weight", d, d, w.wp[i], bwd ? w.wp_t[i] : nullptr);
-        pack(p + "mlp.fc1.weight", 2 * d, d, w.w1[i], bwd ? w.w1_t[i] : nullptr);
-        pack(p + "mlp.fc2.weight", d, 2 * d, w.w2[i], bwd ? w.w2_t[i] : nullptr);
-    }
-    pack("linear.weight", cfg_.clip_length * d, D_, w.wl, nullptr);
+    pack_batch(jobs, s);      // one launch for the whole mapper
 }
 
 void Engine::mapper_forward(const float* params, const MapperW& w, const float* clip, int N, bool save, MapperFwd& f,

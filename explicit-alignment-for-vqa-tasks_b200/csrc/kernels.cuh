@@ -1,6 +1,8 @@
 // Host launchers of the fused memory-bound kernels and the attention kernels.
 // All launch on the given stream and never synchronise.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace eavqa {
@@ -15,6 +17,20 @@ void convert_transpose_f32(const float* src, int ld_src, int R, int C, bf16* dst
                            float* colsum, cudaStream_t s);
 void convert_transpose_bf16(const bf16* src, int ld_src, int R, int C, bf16* dst_t, int ld_t, float* colsum,
                             cudaStream_t s);
+// many fp32 [rows, cols] matrices (dense, ld = cols; even sizes) -> bf16 copies / transposes in ONE launch
+struct PackJob {
+    const float* src;
+    bf16* dst;        // [rows, cols] or null
+    bf16* dst_t;      // [cols, rows] or null
+    int rows, cols;
+    int tile_begin;   // filled by pack_batch
+};
+struct PackJobs {
+    static constexpr int kMax = 48;
+    PackJob job[kMax];
+    int n;
+};
+void pack_batch(const std::vector<PackJob>& jobs, cudaStream_t s);
 // dst[r, :] = src[:]  for r < R   (prefix_const rows of the mapper input), fp32
 void broadcast_rows_f32(const float* src, int rows, int d, float* dst, int64_t batch_stride, int B, cudaStream_t s);
 // out[c] (+)= sum_b src[b*batch_stride + c]   (prefix_const gradient), c < n
