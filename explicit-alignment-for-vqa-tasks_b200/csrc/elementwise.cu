@@ -621,21 +621,28 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
                                                           const float* __restrict__ wte,
                                                           const float* __restrict__ wpe_row, int d,
                                                           float* __restrict__ x_next, int* __restrict__ valid_next,
-                                                          int valid_stride) {
+                                                          int valid_stride, float* __restrict__ part_val,
+                                                          int* __restrict__ part_idx, unsigned* __restrict__ arrivals) {
+    // grid (B, split): every row's vocabulary is scanned by `split` CTAs (one CTA per row left 20 of 148 SMs idle and took
+    // 94 us for 26 MB); each posts its (max, index) and the LAST one to arrive merges them and does the bookkeeping.
     pdl_trigger();
     pdl_wait();
     __shared__ float s_val[8];
     __shared__ int s_idx[8];
     __shared__ int s_next;
     __shared__ float s_best;
+    __shared__ int s_last;
     const int b = blockIdx.x;
+    const int split = gridDim.y, sl = blockIdx.y;
     const float* lp = logits + static_cast<size_t>(b) * ld;
     float best = -INFINITY;
     int best_i = 0x7fffffff;
     // rows are 16-byte aligned (ld % 4 == 0): float4 loads, 4 of them in flight per thread; ties keep the lowest index
     const float4* lp4 = reinterpret_cast<const float4*>(lp);
-    const int n4 = vocab >> 2;
-    for (int v0 = threadIdx.x; v0 < n4; v0 += 4 * blockDim.x) {
+    const int n4_all = vocab >> 2;
+    const int per = (n4_all + split - 1) / split;
+    const int n4_lo = sl * per, n4 = min(n4_all, n4_lo + per);
+    for (int v0 = n4_lo + threadIdx.x; v0 < n4; v0 += 4 * blockDim.x) {
         float4 x[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -651,10 +658,11 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
             if (x[k].w > best) { best = x[k].w; best_i = v + 3; }
         }
     }
-    for (int v = (n4 << 2) + threadIdx.x; v < vocab; v += blockDim.x) {
-        const float x = lp[v];
-        if (x > best || (x == best && v < best_i)) { best = x; best_i = v; }
-    }
+    if (sl == split - 1)
+        for (int v = (n4_all << 2) + threadIdx.x; v < vocab; v += blockDim.x) {
+            const float x = lp[v];
+            if (x > best || (x == best && v < best_i)) { best = x; best_i = v; }
+        }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -676,6 +684,28 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
                 best = s_val[i];
                 best_i = s_idx[i];
             }
+        if (split > 1) {
+            part_val[b * split + sl] = best;
+            part_idx[b * split + sl] = best_i;
+            __threadfence();
+            const unsigned t = atomicAdd(arrivals + b, 1u);
+            s_last = (t == static_cast<unsigned>(split - 1));
+            if (s_last) {
+                __threadfence();
+                arrivals[b] = 0;                                  // ready for the next step
+                for (int i = 0; i < split; ++i) {
+                    const float pv = __ldcg(part_val + b * split + i);
+                    const int pi = __ldcg(part_idx + b * split + i);
+                    if (i == 0 || pv > best || (pv == best && pi < best_i)) { best = pv; best_i = pi; }
+                }
+            }
+        } else {
+            s_last = 1;
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) {
         if (best_i == 0x7fffffff) best_i = 0;
         int unf = unfinished[b];
         int64_t out = best_i;
@@ -1013,9 +1043,14 @@ void ce_dlogits(bf16* z, int ld, int M, int vocab, int n_cols, const float* lse,
 void greedy_step(const float* logits, int ld, int B, int vocab, int step, int max_new, int has_eos, int64_t pad_id,
                  int64_t eos_id, int* unfinished, int64_t* tokens_out, int* n_unfinished, float* top_logit, float* token_logprob,
                  const float* wte, const float* wpe_row, int d, float* x_next, int* valid_next, int valid_stride,
-                 cudaStream_t s) {
-    launch_kernel(greedy_step_kernel, dim3(B), dim3(256), 0, s, logits, ld, vocab, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out,
-                                         n_unfinished, top_logit, token_logprob, wte, wpe_row, d, x_next, valid_next, valid_stride);
+                 float* part_val, int* part_idx, unsigned* arrivals, cudaStream_t s) {
+    // enough CTAs to cover the SMs ~4 times; scratch (part_*, arrivals) is sized for kGreedySplitMax slices per row
+    int split = 1;
+    if (part_val != nullptr && part_idx != nullptr && arrivals != nullptr)
+        split = std::max(1, std::min(kGreedySplitMax, (4 * num_sms()) / std::max(B, 1)));
+    launch_kernel(greedy_step_kernel, dim3(B, split), dim3(256), 0, s, logits, ld, vocab, step, max_new, has_eos, pad_id, eos_id, unfinished,
+                  tokens_out, n_unfinished, top_logit, token_logprob, wte, wpe_row, d, x_next, valid_next, valid_stride, part_val,
+                  part_idx, arrivals);
     KERNEL_CHECK();
     count_launch();
 }

@@ -683,7 +683,9 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     float *prefix = nullptr, *h0 = nullptr, *h1 = nullptr, *h2 = nullptr, *logits = nullptr, *x_a = nullptr, *x_b = nullptr, *x_c = nullptr;
     int *plan = nullptr, *valid0 = nullptr, *validD = nullptr, *row_index = nullptr, *unfinished = nullptr, *flags = nullptr;
     bf16 *u = nullptr, *qkv = nullptr, *att = nullptr, *fc_act = nullptr, *hc = nullptr, *kv = nullptr;
-    float *mean = nullptr, *rstd = nullptr;
+    float *mean = nullptr, *rstd = nullptr, *part_val = nullptr;
+    int* part_idx = nullptr;
+    unsigned* arrivals = nullptr;
     const size_t kv_layer = static_cast<size_t>(B) * Tmax * 2 * d;
     auto plan_all = [&](Arena& a) {
         const size_t m = static_cast<size_t>(M);
@@ -698,6 +700,8 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         logits = a.get<float>(static_cast<size_t>(B) * Vpad_);
         x_a = a.get<float>(static_cast<size_t>(B) * d); x_b = a.get<float>(static_cast<size_t>(B) * d); x_c = a.get<float>(static_cast<size_t>(B) * d);
         unfinished = a.get<int>(B); flags = a.get<int>(max_new + 1);
+        part_val = a.get<float>(static_cast<size_t>(B) * kGreedySplitMax); part_idx = a.get<int>(static_cast<size_t>(B) * kGreedySplitMax);
+        arrivals = a.get<unsigned>(B);
         kv = a.get<bf16>(kv_layer * L);
     };
     {
@@ -717,6 +721,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     int* err_flag = flags + max_new;
     fill_zero(flags, sizeof(int) * (max_new + 1), s);
     fill_zero(validD, sizeof(int) * static_cast<size_t>(B) * Tmax, s);
+    fill_zero(arrivals, sizeof(unsigned) * static_cast<size_t>(B), s);
     launch_kernel(fill_int_kernel, dim3(ceil_div(B, 256)), dim3(256), 0, s, unfinished, B, 1);
     KERNEL_CHECK();
     count_launch();
@@ -756,7 +761,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         gemm(hc, d, wte_bf16_, d, B, Vpad_, d, ep_f32(logits, Vpad_), s);
         greedy_step(logits, Vpad_, B, V_, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out, n_unfinished,
                     top_logit, token_logprob, wte_f32_, wpe_f32_ + static_cast<size_t>(std::min(T0 + step, cfg_.n_positions - 1)) * d, d, x_a,
-                    validD + T0 + step, Tmax, s);
+                    validD + T0 + step, Tmax, part_val, part_idx, arrivals, s);
     };
     head_and_pick(ha, row_index, 0);
 

@@ -7,6 +7,8 @@
 
 namespace eavqa {
 
+constexpr int kGreedySplitMax = 16;    // CTAs per row of the greedy-decode vocabulary scan (scratch sizing)
+
 void count_launch(int n = 1);
 int64_t kernel_launch_count();
 
@@ -79,7 +81,9 @@ void ce_dlogits(bf16* z, int ld, int M, int vocab, int n_cols, const float* lse,
 // tokens_out[b, step] = out; x_next[b] = wte[nxt] + wpe[pos]; n_unfinished[step] = sum(unfinished)
 void greedy_step(const float* logits, int ld, int B, int vocab, int step, int max_new, int has_eos, int64_t pad_id,
                  int64_t eos_id, int* unfinished, int64_t* tokens_out, int* n_unfinished, float* top_logit,
-                 float* token_logprob /* optional: log softmax of the picked token */, const float* wte, const float* wpe_row, int d, float* x_next, int* valid_next, int valid_stride,
+                 float* token_logprob /* optional: log softmax of the picked token */, const float* wte, const float* wpe_row,
+                 int d, float* x_next, int* valid_next, int valid_stride,
+                 float* part_val, int* part_idx, unsigned* arrivals /* scratch [B, kGreedySplitMax] x2 + zeroed [B]; may be null */,
                  cudaStream_t s);
 
 // ---------------------------------------------------------------- executor-side steps (elementwise.cu)
