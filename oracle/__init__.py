@@ -10,5 +10,7 @@ dev container, where ``/root/reference`` exists) checks every function of
 ``oracle/clip_prefix_lm.py`` against the unmodified reference modules
 (``src/models/clipcap.py``, ``src/models/vct0.py``) driving HF ``GPT2LMHeadModel``
 and against the golden tensors of ``src/models/vct0_test.py``, then writes the
-fixtures under ``tests/golden/`` that travel to the GPU box.
+fixtures under ``tests/golden/`` that travel to the GPU box.  ``oracle/executor_steps.py`` (caption labels,
+ensemble scoring) is pinned the same way by ``oracle/validate_executor_steps.py``, which executes the reference's own
+statements (read from ``/root/reference`` at run time) on seeded inputs.
 """
