@@ -176,7 +176,8 @@ int eavqa_op_gemm(const void* A, int32_t lda, const void* B, int32_t ldb, int32_
     API_BEGIN
     GemmArgs a;
     a.A = static_cast<const bf16*>(A); a.lda = lda; a.B = static_cast<const bf16*>(B); a.ldb = ldb;
-    a.M = M; a.N = N; a.K = K; a.block_n = block_n % 1000; a.cluster = block_n / 1000;
+    a.M = M; a.N = N; a.K = K; a.block_n = block_n % 1000; a.cluster = (block_n / 1000) % 100;
+    a.ep.split_k = block_n / 100000;      // > 1: fp32 partials are ADDED into `out` (caller zero-initialises)
     a.ep.out = out; a.ep.ldo = ldo; a.ep.out_fp32 = out_fp32; a.ep.bias = bias; a.ep.residual = residual; a.ep.ld_res = ld_res;
     a.ep.act = act; a.ep.aux = static_cast<const bf16*>(aux); a.ep.ld_aux = ld_aux; a.ep.dact = dact;
     a.ep.out2 = static_cast<bf16*>(out2); a.ep.ldo2 = ldo2;

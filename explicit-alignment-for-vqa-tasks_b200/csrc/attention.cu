@@ -5,7 +5,7 @@
 //    short (T = 50 in training, ~130 in few-shot prefill), so attention is <1% of the step's FLOPs
 //    (SURVEY.md 8d); it is latency/HBM-bound and written for that: one pass over q/k/v, nothing
 //    materialised in HBM but O and the log-sum-exp.
-//  * lm_attention_decode: one query per (batch, head) against the KV cache (HBM-bound streaming).
+//  * lm_attention_decode_acc: one query per (batch, head) against the head-major KV cache (HBM-bound streaming).
 //  * mapper_attention_{fwd,bwd}: the mapper's 8-head, unmasked self-attention over S = 20 rows
 //    (clipcap.py:81-104); fp32 CUDA-core math in shared memory.
 #include <algorithm>
@@ -578,104 +578,117 @@ __global__ void __launch_bounds__(128, 4) lm_attention_bwd_single_kernel(const b
 }
 
 // ------------------------------------------------------------------------------------------ KV cache / decode
+// KV cache of one layer: K block [B, H, Tmax, 64] followed by the V block of the same shape (bf16).  Head-major: the
+// keys / values one (sample, head) attends over are contiguous (Tmax * 128 B), so a decode step streams them with
+// fully coalesced loads and DRAM-page locality (token-major [B, Tmax, 2d] rows cost 29 us per layer for 78 MB).
 __global__ void kv_cache_fill_kernel(const uint4* __restrict__ qkv, uint4* __restrict__ cache, int B, int T, int Tmax,
-                                     int d8) {
+                                     int H) {
     pdl_trigger();
     pdl_wait();
-    // per token row: copy the 2d bf16 (k | v) that follow the d query values
+    const int d8 = H * 8;                                     // uint4 (8 bf16) per d-wide row; 8 per head
     const int64_t total = static_cast<int64_t>(B) * T * 2 * d8;
+    const int64_t vofs = static_cast<int64_t>(B) * H * Tmax * 8;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % (2 * d8));
+        const int c = static_cast<int>(i % (2 * d8));         // 0 .. d8-1: k, d8 .. 2 d8-1: v
         const int64_t row = i / (2 * d8);
         const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
-        cache[(static_cast<int64_t>(b) * Tmax + t) * 2 * d8 + c] = qkv[row * 3 * d8 + d8 + c];
+        const int which = c >= d8, cc = c - which * d8, h = cc >> 3, e = cc & 7;
+        cache[which * vofs + ((static_cast<int64_t>(b) * H + h) * Tmax + t) * 8 + e] = qkv[row * 3 * d8 + d8 + c];
     }
 }
 
-__global__ void __launch_bounds__(128) lm_attention_decode_kernel(const bf16* __restrict__ qkv_new, bf16* __restrict__ cache,
-                                                                  const int* __restrict__ valid, int valid_stride,
-                                                                  bf16* __restrict__ o, int B, int H, int pos, int Tmax) {
+// Split-K decode path: q | k | v arrive as fp32 GEMM accumulators + bias.  One 128-thread CTA per (sample, head); its four
+// warps each take a quarter of the keys (flash-decoding style: per-warp max / sum / partial P.V, merged through shared
+// memory), which quadruples the loads in flight over the one-warp-per-head kernel above (24.6 us per layer for 78 MB).
+__global__ void __launch_bounds__(128) lm_attention_decode_acc_kernel(const float* __restrict__ qkv_acc, const float* __restrict__ qkv_bias,
+                                                                      bf16* __restrict__ cache, const int* __restrict__ valid,
+                                                                      int valid_stride, bf16* __restrict__ o, float* __restrict__ zero,
+                                                                      int H, int pos, int Tmax) {
     pdl_trigger();
     pdl_wait();
-    // One warp per (sample, head).  Scores: lanes over keys (each lane dots whole 128-B key rows, 8 independent 16-B
-    // loads in flight).  P.V: 4 keys per iteration, 8 lanes x 16 B per value row, partial sums folded by two shuffles
-    // -- the first version walked the values one key at a time (150 dependent iterations, 40 us per layer).
-    extern __shared__ float sc[];     // [4 warps][Tmax] scores
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bh = blockIdx.x * 4 + warp;
-    if (bh >= B * H) return;
-    const int b = bh / H, h = bh % H;
+    extern __shared__ float sc[];     // [Tmax] scores / probabilities
+    __shared__ __align__(16) float sq[HD];
+    __shared__ float part[4][HD];
+    __shared__ float part_m[4], part_l[4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int d = H * HD;
-    float* s = sc + warp * Tmax;
-    const bf16* qrow = qkv_new + static_cast<int64_t>(b) * 3 * d + h * HD;
-    bf16* crow = cache + static_cast<int64_t>(b) * Tmax * 2 * d;
-    {   // append this step's k, v (2 elements per lane each)
-        const uint32_t kk = *reinterpret_cast<const uint32_t*>(qrow + d + 2 * lane);
-        const uint32_t vv = *reinterpret_cast<const uint32_t*>(qrow + 2 * d + 2 * lane);
-        *reinterpret_cast<uint32_t*>(crow + static_cast<int64_t>(pos) * 2 * d + h * HD + 2 * lane) = kk;
-        *reinterpret_cast<uint32_t*>(crow + static_cast<int64_t>(pos) * 2 * d + d + h * HD + 2 * lane) = vv;
+    const float* arow = qkv_acc + static_cast<int64_t>(b) * 3 * d;
+    const int B = gridDim.x / H;
+    bf16* kbase = cache + (static_cast<int64_t>(b) * H + h) * Tmax * HD;                  // this head's keys [Tmax, 64]
+    bf16* vhead = kbase + static_cast<int64_t>(B) * H * Tmax * HD;                        // ... and values
+    if (tid < HD) {
+        const int c = h * HD + tid;
+        sq[tid] = (arow[c] + __ldg(qkv_bias + c)) * 0.125f;                              // head_dim ** -0.5 folded into q
+        kbase[static_cast<int64_t>(pos) * HD + tid] = __float2bfloat16(arow[d + c] + __ldg(qkv_bias + d + c));
+        if (zero != nullptr) zero[static_cast<int64_t>(b) * d + c] = 0.f;
+    } else {
+        const int c = h * HD + tid - HD;
+        vhead[static_cast<int64_t>(pos) * HD + tid - HD] = __float2bfloat16(arow[2 * d + c] + __ldg(qkv_bias + 2 * d + c));
     }
-    __syncwarp();
-    float q[HD];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint4 u = *reinterpret_cast<const uint4*>(qrow + c * 8);
-        float2 f;
-        f = unpack_bf16x2(u.x); q[c * 8 + 0] = f.x; q[c * 8 + 1] = f.y;
-        f = unpack_bf16x2(u.y); q[c * 8 + 2] = f.x; q[c * 8 + 3] = f.y;
-        f = unpack_bf16x2(u.z); q[c * 8 + 4] = f.x; q[c * 8 + 5] = f.y;
-        f = unpack_bf16x2(u.w); q[c * 8 + 6] = f.x; q[c * 8 + 7] = f.y;
-    }
+    __syncthreads();
+    // q stays in shared memory (broadcast LDS.128 in the dot products): 64 fewer registers per thread -> twice the CTAs
+    // per SM, and this kernel is bound by (load latency x waves of CTAs), not by instruction issue
     const int n = pos + 1;
+    const int chunk = (n + 3) >> 2;
+    const int t0 = warp * chunk, t1 = min(n, t0 + chunk);
     float mx = -INFINITY;
-    for (int t = lane; t < n; t += 32) {
+    for (int t = t0 + lane; t < t1; t += 32) {
         float acc = -INFINITY;
         if (valid[static_cast<int64_t>(b) * valid_stride + t]) {
-            const uint4* kp = reinterpret_cast<const uint4*>(crow + static_cast<int64_t>(t) * 2 * d + h * HD);
+            const uint4* kp = reinterpret_cast<const uint4*>(kbase + static_cast<int64_t>(t) * HD);
             uint4 u[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) u[c] = kp[c];
             acc = 0.f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
+                const float4 qa = *reinterpret_cast<const float4*>(sq + c * 8), qb = *reinterpret_cast<const float4*>(sq + c * 8 + 4);
                 float2 f;
-                f = unpack_bf16x2(u[c].x); acc += q[c * 8 + 0] * f.x + q[c * 8 + 1] * f.y;
-                f = unpack_bf16x2(u[c].y); acc += q[c * 8 + 2] * f.x + q[c * 8 + 3] * f.y;
-                f = unpack_bf16x2(u[c].z); acc += q[c * 8 + 4] * f.x + q[c * 8 + 5] * f.y;
-                f = unpack_bf16x2(u[c].w); acc += q[c * 8 + 6] * f.x + q[c * 8 + 7] * f.y;
+                f = unpack_bf16x2(u[c].x); acc += qa.x * f.x + qa.y * f.y;
+                f = unpack_bf16x2(u[c].y); acc += qa.z * f.x + qa.w * f.y;
+                f = unpack_bf16x2(u[c].z); acc += qb.x * f.x + qb.y * f.y;
+                f = unpack_bf16x2(u[c].w); acc += qb.z * f.x + qb.w * f.y;
             }
-            acc *= 0.125f;
         }
-        s[t] = acc;
+        sc[t] = acc;
         mx = fmaxf(mx, acc);
     }
     mx = warp_max(mx);
-    if (mx == -INFINITY) mx = 0.f;
+    const float muse = (mx == -INFINITY) ? 0.f : mx;
     float sum = 0.f;
-    for (int t = lane; t < n; t += 32) {
-        const float p = __expf(s[t] - mx);
-        s[t] = p;
+    for (int t = t0 + lane; t < t1; t += 32) {
+        const float p = __expf(sc[t] - muse);
+        sc[t] = p;
         sum += p;
     }
     sum = warp_sum(sum);
     __syncwarp();
-    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-    // P.V: lane = (key slot ks = lane / 8, column group cg = lane % 8 -> columns 8 cg .. 8 cg + 7)
     const int ks = lane >> 3, cg = lane & 7;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const bf16* vbase = crow + d + h * HD + cg * 8;
-#pragma unroll 4
-    for (int t = ks; t < n; t += 4) {
-        const float p = s[t];
-        const uint4 u = *reinterpret_cast<const uint4*>(vbase + static_cast<int64_t>(t) * 2 * d);
-        float2 f;
-        f = unpack_bf16x2(u.x); acc[0] += p * f.x; acc[1] += p * f.y;
-        f = unpack_bf16x2(u.y); acc[2] += p * f.x; acc[3] += p * f.y;
-        f = unpack_bf16x2(u.z); acc[4] += p * f.x; acc[5] += p * f.y;
-        f = unpack_bf16x2(u.w); acc[6] += p * f.x; acc[7] += p * f.y;
+    const bf16* vbase = vhead + cg * 8;
+    // 8 value rows per lane in flight (the warp covers 32 keys per iteration with 512-byte coalesced requests)
+    for (int t = t0 + ks; t < t1; t += 32) {
+        uint4 u[8];
+        float p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int tt = t + 4 * i;
+            const bool ok = tt < t1;
+            u[i] = ok ? *reinterpret_cast<const uint4*>(vbase + static_cast<int64_t>(tt) * HD) : make_uint4(0u, 0u, 0u, 0u);
+            p[i] = ok ? sc[tt] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float2 f;
+            f = unpack_bf16x2(u[i].x); acc[0] += p[i] * f.x; acc[1] += p[i] * f.y;
+            f = unpack_bf16x2(u[i].y); acc[2] += p[i] * f.x; acc[3] += p[i] * f.y;
+            f = unpack_bf16x2(u[i].z); acc[4] += p[i] * f.x; acc[5] += p[i] * f.y;
+            f = unpack_bf16x2(u[i].w); acc[6] += p[i] * f.x; acc[7] += p[i] * f.y;
+        }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -683,12 +696,26 @@ __global__ void __launch_bounds__(128) lm_attention_decode_kernel(const bf16* __
         acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
     }
     if (ks == 0) {
-        uint4 out;
-        out.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
-        out.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-        out.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
-        out.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
-        *reinterpret_cast<uint4*>(o + static_cast<int64_t>(b) * d + h * HD + cg * 8) = out;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) part[warp][cg * 8 + i] = acc[i];
+    }
+    if (lane == 0) {
+        part_m[warp] = mx;
+        part_l[warp] = sum;
+    }
+    __syncthreads();
+    if (tid < HD) {
+        const float m = fmaxf(fmaxf(part_m[0], part_m[1]), fmaxf(part_m[2], part_m[3]));
+        float l = 0.f, v = 0.f;
+        if (m > -INFINITY) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float sw = (part_m[w] == -INFINITY) ? 0.f : __expf(part_m[w] - m);
+                l += part_l[w] * sw;
+                v += part[w][tid] * sw;
+            }
+        }
+        o[static_cast<int64_t>(b) * d + h * HD + tid] = __float2bfloat16(l > 0.f ? v / l : 0.f);
     }
 }
 
@@ -1114,21 +1141,20 @@ void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf
 }
 
 void kv_cache_fill(const bf16* qkv, bf16* cache, int B, int T, int Tmax, int d, cudaStream_t s) {
-    EAVQA_CHECK(d % 8 == 0, "kv cache width");
+    EAVQA_CHECK(d % HD == 0, "kv_cache_fill: d must be a multiple of the head size");
     const int64_t total = static_cast<int64_t>(B) * T * 2 * (d / 8);
-    const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 148 * 16));
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), static_cast<int64_t>(num_sms()) * 8));
     launch_kernel(kv_cache_fill_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const uint4*>(qkv), reinterpret_cast<uint4*>(cache), B, T,
-                                              Tmax, d / 8);
+                  Tmax, d / HD);
     KERNEL_CHECK();
     count_launch();
 }
-
-void lm_attention_decode(const bf16* qkv_new, bf16* cache, const int* valid, int valid_stride, bf16* o, int B, int H,
-                         int pos, int Tmax, cudaStream_t s) {
-    const int smem = 4 * Tmax * sizeof(float);
-    EAVQA_CHECK(smem <= 48 * 1024, "decode attention: sequence too long for the score buffer");
-    EAVQA_CHECK(pos < Tmax, "decode position beyond the KV cache");
-    launch_kernel(lm_attention_decode_kernel, dim3(ceil_div(B * H, 4)), dim3(128), smem, s, qkv_new, cache, valid, valid_stride, o, B, H, pos, Tmax);
+void lm_attention_decode_acc(const float* qkv_acc, const float* qkv_bias, bf16* cache, const int* valid, int valid_stride, bf16* o,
+                             float* zero, int B, int H, int pos, int Tmax, cudaStream_t s) {
+    const size_t smem = sizeof(float) * Tmax;
+    EAVQA_CHECK(smem <= 40 * 1024, "decode: KV length exceeds the score buffer");
+    launch_kernel(lm_attention_decode_acc_kernel, dim3(B * H), dim3(128), smem, s, qkv_acc, qkv_bias, cache, valid, valid_stride, o, zero, H,
+                  pos, Tmax);
     KERNEL_CHECK();
     count_launch();
 }

@@ -185,6 +185,97 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------ single-token decode glue
+// Decode steps run their M = batch-row GEMMs split along K over all SMs, accumulating fp32 partials into scratch rows
+// (profiles/: unsplit, the projections used 16 of 148 SMs and took 16-20 us each).  These two kernels are what sits
+// between those GEMMs: they apply bias / residual / LayerNorm / gelu to the accumulated rows and zero the scratch rows
+// of the NEXT GEMM.  One 128-thread CTA per row.
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();                       // red may still be read from the previous reduction
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+}
+
+// x[row] += acc[row] + bias (when acc != null); u[row] = LN(x[row]) * gamma + beta (bf16); zero[row, 0..zero_n) = 0
+__global__ void __launch_bounds__(128) decode_residual_ln_kernel(float* __restrict__ x, const float* __restrict__ acc,
+                                                                 const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, bf16* __restrict__ u, int d,
+                                                                 float eps, float* __restrict__ zero, int zero_n) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[4];
+    const int row = blockIdx.x, n4 = d >> 2;
+    float4* xp = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * d);
+    float4 v[4];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + 128 * i;
+        if (c < n4) {
+            v[i] = xp[c];
+            if (acc != nullptr) {
+                const float4 a = reinterpret_cast<const float4*>(acc + static_cast<size_t>(row) * d)[c];
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c);
+                v[i].x += a.x + b.x; v[i].y += a.y + b.y; v[i].z += a.z + b.z; v[i].w += a.w + b.w;
+                xp[c] = v[i];
+            }
+            sum += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    }
+    const float mean = block_sum_128(sum, red) / d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + 128 * i;
+        if (c < n4) {
+            const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+            sq += a * a + b * b + e * e + f * f;
+        }
+    }
+    const float rstd = rsqrtf(block_sum_128(sq, red) / d + eps);
+    uint2* up = reinterpret_cast<uint2*>(u + static_cast<size_t>(row) * d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + 128 * i;
+        if (c < n4) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c), b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+            uint2 o;
+            o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+            o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+            up[c] = o;
+        }
+    }
+    if (zero != nullptr) {
+        float4* zp = reinterpret_cast<float4*>(zero + static_cast<size_t>(row) * zero_n);
+        for (int c = threadIdx.x; c < (zero_n >> 2); c += 128) zp[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// out[row] = gelu_new(acc[row] + bias) (bf16, n columns); zero[row, 0..zero_n) = 0
+__global__ void __launch_bounds__(128) decode_bias_gelu_kernel(const float* __restrict__ acc, const float* __restrict__ bias,
+                                                               bf16* __restrict__ out, int n, float* __restrict__ zero, int zero_n) {
+    pdl_trigger();
+    pdl_wait();
+    const int row = blockIdx.x;
+    const float4* ap = reinterpret_cast<const float4*>(acc + static_cast<size_t>(row) * n);
+    uint2* op = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * n);
+    for (int c = threadIdx.x; c < (n >> 2); c += 128) {
+        const float4 a = ap[c];
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c);
+        uint2 o;
+        o.x = pack_bf16x2(gelu_new(a.x + b.x), gelu_new(a.y + b.y));
+        o.y = pack_bf16x2(gelu_new(a.z + b.z), gelu_new(a.w + b.w));
+        op[c] = o;
+    }
+    if (zero != nullptr) {
+        float4* zp = reinterpret_cast<float4*>(zero + static_cast<size_t>(row) * zero_n);
+        for (int c = threadIdx.x; c < (zero_n >> 2); c += 128) zp[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 template <int MAXV, bool PARAM_GRADS>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, int ld_dy,
                                                             const float* __restrict__ x, int ld_x,
@@ -934,6 +1025,21 @@ void layernorm_fwd(const float* x, int ld_x, const int* row_index, const float* 
     else if (need <= 13) EAVQA_LN_FWD(13);
     else EAVQA_LN_FWD(16);
 #undef EAVQA_LN_FWD
+    KERNEL_CHECK();
+    count_launch();
+}
+
+void decode_residual_ln(float* x, const float* acc, const float* bias, const float* gamma, const float* beta, bf16* u, int rows, int d,
+                        float eps, float* zero, int zero_n, cudaStream_t s) {
+    EAVQA_CHECK(d % 4 == 0 && d <= 2048 && zero_n % 4 == 0, "decode_residual_ln: width must be a multiple of 4 and <= 2048");
+    EAVQA_CHECK((acc == nullptr) == (bias == nullptr), "decode_residual_ln: acc and bias come together");
+    launch_kernel(decode_residual_ln_kernel, dim3(rows), dim3(128), 0, s, x, acc, bias, gamma, beta, u, d, eps, zero, zero_n);
+    KERNEL_CHECK();
+    count_launch();
+}
+void decode_bias_gelu(const float* acc, const float* bias, bf16* out, int rows, int n, float* zero, int zero_n, cudaStream_t s) {
+    EAVQA_CHECK(n % 4 == 0 && zero_n % 4 == 0, "decode_bias_gelu: widths must be multiples of 4");
+    launch_kernel(decode_bias_gelu_kernel, dim3(rows), dim3(128), 0, s, acc, bias, out, n, zero, zero_n);
     KERNEL_CHECK();
     count_launch();
 }

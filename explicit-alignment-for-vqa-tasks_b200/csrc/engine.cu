@@ -4,6 +4,7 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 
@@ -59,6 +60,17 @@ void gemm_wgrad(const bf16* At, int ldat, const bf16* Bt, int ldbt, int M, int N
     split = std::max(1, std::min(split, std::min(8, kb / 4)));
     a.block_n = bn;
     a.ep.split_k = split;
+    gemm_bf16_tn(a, s);
+}
+// single-token decode: acc[M, N] (fp32, pre-zeroed) += A[M, K] * W[N, K]^T with K split so that ~all SMs stream weights
+// (tools/decode_gemm_bench.py on B200: 1024 x 4096 weights for 128 rows 20.1 -> 6.6 us, 1024 x 1024 8.0 -> 5.4 us)
+void gemm_decode(const bf16* A, int lda, const bf16* W, int ldb, int M, int N, int K, float* acc, cudaStream_t s) {
+    GemmArgs a;
+    a.A = A; a.lda = lda; a.B = W; a.ldb = ldb; a.M = M; a.N = N; a.K = K; a.block_n = 64; a.cluster = 1;
+    a.ep.out = acc; a.ep.ldo = N; a.ep.out_fp32 = 1;
+    const int tiles = ceil_div(M, 128) * ceil_div(N, 64), kb = ceil_div(K, 64);
+    int split = (num_sms() * 7 / 8 + tiles / 2) / std::max(tiles, 1);
+    a.ep.split_k = std::max(1, std::min(split, std::max(1, kb / 2)));
     gemm_bf16_tn(a, s);
 }
 GemmEpilogue ep_bf16(bf16* out, int ldo, const float* bias = nullptr) {
@@ -511,10 +523,8 @@ struct LmBlockIO {
     float *lse, *mean1, *rstd1, *mean2, *rstd2;
     bf16 *fc_pre, *fc_act;
     // generation
-    bf16* kv_cache = nullptr;   // this layer's cache [B, Tmax, 2d]
+    bf16* kv_cache = nullptr;   // this layer's cache (K block [B, H, Tmax, 64] + V block), filled during prefill
     int Tmax = 0;
-    int decode_pos = -1;        // >= 0: single-token step attending over the cache
-    int valid_stride = 0;
 };
 
 static void lm_block(const LmLayer& w, int d, int H, const LmBlockIO& io, cudaStream_t s) {
@@ -522,12 +532,8 @@ static void lm_block(const LmLayer& w, int d, int H, const LmBlockIO& io, cudaSt
     // HF modeling_gpt2.py:262-309
     layernorm_fwd(io.h_in, d, nullptr, w.ln1_g, w.ln1_b, io.u, d, io.mean1, io.rstd1, M, d, 1e-5f, s);
     gemm(io.u, d, w.w_qkv_t, d, M, 3 * d, d, ep_bf16(io.qkv, 3 * d, w.b_qkv), s);
-    if (io.decode_pos >= 0) {
-        lm_attention_decode(io.qkv, io.kv_cache, io.valid, io.valid_stride, io.att, io.B, H, io.decode_pos, io.Tmax, s);
-    } else {
-        if (io.kv_cache != nullptr) kv_cache_fill(io.qkv, io.kv_cache, io.B, io.T, io.Tmax, d, s);
-        lm_attention_fwd(io.qkv, io.valid, io.att, io.lse, io.B, io.T, H, s);
-    }
+    if (io.kv_cache != nullptr) kv_cache_fill(io.qkv, io.kv_cache, io.B, io.T, io.Tmax, d, s);     // prefill
+    lm_attention_fwd(io.qkv, io.valid, io.att, io.lse, io.B, io.T, H, s);
     gemm(io.att, d, w.w_o_t, d, M, d, d, ep_f32(io.h_mid, d, w.b_o, io.h_in, d), s);
     layernorm_fwd(io.h_mid, d, nullptr, w.ln2_g, w.ln2_b, io.u, d, io.mean2, io.rstd2, M, d, 1e-5f, s);
     GemmEpilogue e = ep_bf16(io.fc_act, 4 * d, w.b_fc);
@@ -666,6 +672,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
                       int64_t sent_lo, int64_t sent_hi, const float* params, int max_new, int has_eos, int64_t pad_id,
                       int64_t eos_id, int64_t* tokens_out, float* top_logit, float* token_logprob, int32_t* steps_out,
                       cudaStream_t s) {
+    const auto t_begin = std::chrono::steady_clock::now();
     EAVQA_CHECK(finalized_, "LM weights not loaded (call eavqa_finalize_lm)");
     EAVQA_CHECK(B > 0 && Tt > 0 && max_new > 0, "empty batch / max_length");
     EAVQA_CHECK(clip && tokens && params && tokens_out && steps_out, "null argument");
@@ -684,6 +691,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     int *plan = nullptr, *valid0 = nullptr, *validD = nullptr, *row_index = nullptr, *unfinished = nullptr, *flags = nullptr;
     bf16 *u = nullptr, *qkv = nullptr, *att = nullptr, *fc_act = nullptr, *hc = nullptr, *kv = nullptr;
     float *mean = nullptr, *rstd = nullptr, *part_val = nullptr;
+    float *acc_qkv = nullptr, *acc_o = nullptr, *acc_fc = nullptr, *acc_pr = nullptr;     // split-K accumulators of the decode steps
     int* part_idx = nullptr;
     unsigned* arrivals = nullptr;
     const size_t kv_layer = static_cast<size_t>(B) * Tmax * 2 * d;
@@ -702,6 +710,8 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         unfinished = a.get<int>(B); flags = a.get<int>(max_new + 1);
         part_val = a.get<float>(static_cast<size_t>(B) * kGreedySplitMax); part_idx = a.get<int>(static_cast<size_t>(B) * kGreedySplitMax);
         arrivals = a.get<unsigned>(B);
+        acc_qkv = a.get<float>(static_cast<size_t>(B) * 3 * d); acc_o = a.get<float>(static_cast<size_t>(B) * d);
+        acc_fc = a.get<float>(static_cast<size_t>(B) * 4 * d); acc_pr = a.get<float>(static_cast<size_t>(B) * d);
         kv = a.get<bf16>(kv_layer * L);
     };
     {
@@ -756,36 +766,49 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     launch_kernel(last_row_index_kernel, dim3(ceil_div(B, 256)), dim3(256), 0, s, row_index, B, T0);
     KERNEL_CHECK();
     count_launch();
-    auto head_and_pick = [&](const float* hidden, const int* rows, int step) {
-        layernorm_fwd(hidden, d, rows, lnf_g_, lnf_b_, hc, d, nullptr, nullptr, B, d, 1e-5f, s);
+    auto head_and_pick = [&](int step) {       // hc = ln_f(last hidden) -> logits -> greedy token, next input embedding in x_a
         gemm(hc, d, wte_bf16_, d, B, Vpad_, d, ep_f32(logits, Vpad_), s);
         greedy_step(logits, Vpad_, B, V_, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out, n_unfinished,
                     top_logit, token_logprob, wte_f32_, wpe_f32_ + static_cast<size_t>(std::min(T0 + step, cfg_.n_positions - 1)) * d, d, x_a,
                     validD + T0 + step, Tmax, part_val, part_idx, arrivals, s);
     };
-    head_and_pick(ha, row_index, 0);
+    layernorm_fwd(ha, d, row_index, lnf_g_, lnf_b_, hc, d, nullptr, nullptr, B, d, 1e-5f, s);
+    head_and_pick(0);
 
-    // ---- decode: one token per row per step against the KV cache (the reference re-runs the whole
-    //      sequence each step, clipcap.py:416-419; same function, 11x less work)
+    // ---- decode: one token per row per step against the KV cache (the reference re-runs the whole sequence each
+    //      step, clipcap.py:416-419; same function, 11x less work).  M = B rows per GEMM: every projection is split along K
+    //      over all SMs into fp32 accumulators; bias / residual / LayerNorm / gelu live in the small kernels between them,
+    //      each of which also zeroes the accumulator of the GEMM that follows.  x_a is the fp32 residual row.
+    (void)x_b; (void)x_c;
     for (int step = 1; step < max_new; ++step) {
         const int pos = T0 + step - 1;
-        float *xin = x_a, *xmid = x_b, *xout = x_c;
+        decode_residual_ln(x_a, nullptr, nullptr, layers_[0].ln1_g, layers_[0].ln1_b, u, B, d, 1e-5f, acc_qkv, 3 * d, s);
         for (int l = 0; l < L; ++l) {
-            LmBlockIO io;
-            io.l = l; io.M = B; io.B = B; io.T = 1;
-            io.h_in = xin; io.h_mid = xmid; io.h_out = xout;
-            io.valid = validD; io.u = u; io.qkv = qkv; io.att = att; io.lse = nullptr;
-            io.mean1 = mean; io.rstd1 = rstd; io.mean2 = mean; io.rstd2 = rstd;
-            io.fc_pre = nullptr; io.fc_act = fc_act;
-            io.kv_cache = kv + kv_layer * l; io.Tmax = Tmax; io.decode_pos = pos; io.valid_stride = Tmax;
-            lm_block(layers_[l], d, H_, io, s);
-            float* t = xin; xin = xout; xout = xmid; xmid = t;
+            const LmLayer& w = layers_[l];
+            gemm_decode(u, d, w.w_qkv_t, d, B, 3 * d, d, acc_qkv, s);
+            lm_attention_decode_acc(acc_qkv, w.b_qkv, kv + kv_layer * l, validD, Tmax, att, acc_o, B, H_, pos, Tmax, s);
+            gemm_decode(att, d, w.w_o_t, d, B, d, d, acc_o, s);
+            decode_residual_ln(x_a, acc_o, w.b_o, w.ln2_g, w.ln2_b, u, B, d, 1e-5f, acc_fc, 4 * d, s);
+            gemm_decode(u, d, w.w_fc_t, d, B, 4 * d, d, acc_fc, s);
+            decode_bias_gelu(acc_fc, w.b_fc, fc_act, B, 4 * d, acc_pr, d, s);
+            gemm_decode(fc_act, 4 * d, w.w_pr_t, 4 * d, B, d, 4 * d, acc_pr, s);
+            if (l + 1 < L)
+                decode_residual_ln(x_a, acc_pr, w.b_pr, layers_[l + 1].ln1_g, layers_[l + 1].ln1_b, u, B, d, 1e-5f, acc_qkv, 3 * d, s);
+            else
+                decode_residual_ln(x_a, acc_pr, w.b_pr, lnf_g_, lnf_b_, hc, B, d, 1e-5f, nullptr, 0, s);
         }
-        // xin holds the final hidden state; ln_f consumes it before greedy_step overwrites x_a (stream order)
-        head_and_pick(xin, nullptr, step);
+        head_and_pick(step);
     }
     CUDA_CHECK(cudaMemcpyAsync(host_flags_, flags, sizeof(int) * (max_new + 1), cudaMemcpyDeviceToHost, s));
+    static const bool timing = getenv("EAVQA_TIMING") != nullptr;
+    const auto t_enq = std::chrono::steady_clock::now();
     CUDA_CHECK(cudaStreamSynchronize(s));
+    if (timing) {
+        const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "[eavqa] generate: host enqueue %.3f ms, then waited %.3f ms for the GPU\n",
+                std::chrono::duration<double, std::milli>(t_enq - t_begin).count(),
+                std::chrono::duration<double, std::milli>(t_end - t_enq).count());
+    }
     EAVQA_CHECK(host_flags_[max_new] == 0,
                 "prompt rows must each hold exactly n_images sentinel tokens (vct0.py:512 would fail its .view)");
     int steps = max_new;

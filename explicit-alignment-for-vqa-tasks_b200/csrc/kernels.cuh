@@ -53,6 +53,13 @@ void layernorm_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, const in
 void layernorm_param_grads(const bf16* dy, int ld_dy, const float* x, int ld_x, const float* mean, const float* rstd,
                            float* dgamma, float* dbeta, int M, int d, cudaStream_t s);
 
+// ---------------------------------------------------------------- single-token decode glue (elementwise.cu)
+// x[row] += acc[row] + bias (acc, bias may both be null); u[row] = LN(x[row]) (bf16); zero[row, 0..zero_n) = 0 (may be null)
+void decode_residual_ln(float* x, const float* acc, const float* bias, const float* gamma, const float* beta, bf16* u, int rows, int d,
+                        float eps, float* zero, int zero_n, cudaStream_t s);
+// out[row] = gelu_new(acc[row] + bias) (bf16 [rows, n]); zero[row, 0..zero_n) = 0 (may be null)
+void decode_bias_gelu(const float* acc, const float* bias, bf16* out, int rows, int n, float* zero, int zero_n, cudaStream_t s);
+
 // ---------------------------------------------------------------- embedding / splice (elementwise.cu)
 // plan[b, t] >= 0 : token id ; < 0 : -(prefix_row + 1) ; valid[b, t] = key-validity (attention mask)
 void prepend_plan(const int64_t* tokens, const int64_t* mask, int B, int Tt, int P, int* plan, int* valid, cudaStream_t s);
@@ -109,11 +116,13 @@ void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, in
 // dqkv [B*T, 3d] bf16; dq_scratch fp32 [B*T, d] (only touched when T > 64)
 void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf16* d_o, const float* lse, bf16* dqkv,
                       float* dq_scratch, int B, int T, int H, cudaStream_t s);
-// KV cache: [B, Tmax, 2d] bf16 per layer (k | v per token)
+// KV cache per layer: K block [B, H, Tmax, 64] then V block [B, H, Tmax, 64] (bf16, head-major)
 void kv_cache_fill(const bf16* qkv, bf16* cache, int B, int T, int Tmax, int d, cudaStream_t s);
-// one new query per (b, h): appends this step's k, v at position pos and attends over keys [0, pos] where valid
-void lm_attention_decode(const bf16* qkv_new, bf16* cache, const int* valid, int valid_stride, bf16* o, int B, int H,
-                         int pos, int Tmax, cudaStream_t s);
+// one new query per (b, h): q | k | v given as fp32 GEMM accumulators [B, 3d] + bias [3d] (split-K decode path); appends this
+// step's k, v at position pos and attends over keys [0, pos] where valid; four warps per (sample, head) share the keys;
+// also zeroes zero[b, h*64 .. h*64+64) (the next GEMM's accumulator rows, [B, d])
+void lm_attention_decode_acc(const float* qkv_acc, const float* qkv_bias, bf16* cache, const int* valid, int valid_stride, bf16* o,
+                             float* zero, int B, int H, int pos, int Tmax, cudaStream_t s);
 
 // mapper self-attention (no mask), S = clip_length + prefix_length small, any head_dim: qkv [B*S, 3d] bf16
 void mapper_attention_fwd(const bf16* qkv, bf16* o, int B, int S, int H, int hd, cudaStream_t s);

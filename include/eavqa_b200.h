@@ -142,7 +142,8 @@ int eavqa_profile_end(double* total_ms, double* total_flops, int64_t* launches, 
 
 /* ---- single-operator entry points (unit parity tests of each kernel; same kernels the step uses) ---- */
 /* D[M,N] = epi(A[M,K] * B[N,K]^T): bf16 operands, fp32 accumulate (tcgen05/TMEM); act/dact: see csrc/gemm.cuh.
- * block_n = tile width (0 = auto, 64/128/192/256) + 1000 * cta_mode (0 = auto, 1 = single CTAs, 8 = CTA pair / cta_group::2).
+ * block_n = tile width (0 = auto, 64/128/192/256) + 1000 * cta_mode (0 = auto, 1 = single CTAs, 8 = CTA pair / cta_group::2)
+ *           + 100000 * split_k (> 1: K is split over that many CTAs per tile which ADD fp32 partials into a zeroed `out`).
  * Supported epilogues (csrc/gemm_kernel.cuh, EpiMode): bf16 out [+bias] [+gelu_new (+pre-activation out2) | relu | tanh];
  * bf16 out = acc * f'(aux) (dact, no bias); fp32 out [+bias [+residual]].  Other combinations return an error. */
 int eavqa_op_gemm(const void* A, int32_t lda, const void* B, int32_t ldb, int32_t M, int32_t N, int32_t K, void* out,
