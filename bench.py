@@ -151,6 +151,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version line to STDOUT, next to the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import eavqa_b200
