@@ -32,7 +32,17 @@ C2 = dict(model_version="gpt2", mapping_type="transformer", prefix_length=10, cl
           batch_per_gpu=256, text_len=40, vocab=50257)
 C4 = dict(model_version="gpt2-medium", mapping_type="mlp", prefix_length=10, clip_length=10, clip_dim=512, num_layers=8,
           batch=128, num_shots=4, max_length=10)
+C5 = dict(model_version="gpt2-xl", mapping_type="mlp", prefix_length=10, clip_length=10, clip_dim=768, num_layers=8,
+          batch_per_gpu=64, text_len=40, vocab=50257)
 GFLOP_PER_SAMPLE_C2 = 27.88          # algorithmic work per sample: LM 23.30 + transformer mapper 4.58
+GFLOP_PER_SAMPLE = {"c2": 27.88, "c5": 309.7}       # c5: LM 308.9 + MLP mapper 0.79
+WORKLOAD_TEXT = {
+    "c2": "Conceptual Captions mapper training step, BASELINE configs[1]: frozen GPT-2 small (d=768, L=12, V=50257), "
+          "transformer mapper (8 layers, 8 heads, clip_length 10), prefix 10, text 40 (T=50), synthetic CLIP ViT-B/32 512-d embeddings",
+    "c5": "Large-LM scaling, BASELINE configs[4]: frozen GPT-2 XL (d=1600, L=48, H=25, V=50257), MLP mapper, prefix 10, text 40 "
+          "(T=50), synthetic CLIP ViT-L/14 768-d embeddings, 64 samples per GPU (512 on 8 GPUs)",
+}
+WORKLOAD = "c2"
 CPU_SAMPLE_BATCH = 8                 # bounded CPU sample: the same config at batch 8
 
 
@@ -121,9 +131,8 @@ def run_reference(args, rank):
 
 
 def workload_config(world, note=""):
-    return {"workload": "Conceptual Captions mapper training step, BASELINE configs[1]: frozen GPT-2 small (d=768, L=12, V=50257), "
-                        "transformer mapper (8 layers, 8 heads, clip_length 10), prefix 10, text 40 (T=50), synthetic CLIP ViT-B/32 "
-                        "512-d embeddings", "batch_per_gpu": C2["batch_per_gpu"], "global_batch": C2["batch_per_gpu"] * world,
+    W = C5 if WORKLOAD == "c5" else C2
+    return {"workload": WORKLOAD_TEXT[WORKLOAD], "batch_per_gpu": W["batch_per_gpu"], "global_batch": W["batch_per_gpu"] * world,
             "parallelism": "dp%d" % world, "optimizer": "fused AdamW on the mapper (in the timed region)",
             "l2": "inputs larger than L2: ~3 GB of activations per step >> 126 MB L2, no flush needed", "note": note}
 
@@ -138,7 +147,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-report", default="", help="write the per-shape GEMM timing report to this file")
     ap.add_argument("--only-timed", action="store_true", help="run only warm-up + the timed region (for ncu launch lists)")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="N > 1: bucketed gradient all-reduce overlapped with the mapper backward (measured slower; see DESIGN.md)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 = BASELINE configs[1] (the metric's configuration, default); c5 = configs[4], GPT-2 XL, 64 samples / GPU")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
+    W = C5 if WORKLOAD == "c5" else C2
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -161,24 +177,32 @@ def main():
     from eavqa_b200.optim import FlatAdamW
     L = lib.load()
 
-    lm_cfg = syn.lm_config(C2["model_version"], vocab=C2["vocab"])
+    lm_cfg = syn.lm_config(W["model_version"], vocab=W["vocab"])
     lm_w = syn.make_lm_weights(lm_cfg, seed=0)
     torch.manual_seed(1)
-    model = eavqa_b200.ClipCaptionPrefixB200(prefix_length=C2["prefix_length"], clip_length=C2["clip_length"],
-                                             prefix_size=C2["clip_dim"], num_layers=C2["num_layers"],
-                                             mapping_type=C2["mapping_type"], model_version=C2["model_version"],
+    model = eavqa_b200.ClipCaptionPrefixB200(prefix_length=W["prefix_length"], clip_length=W["clip_length"],
+                                             prefix_size=W["clip_dim"], num_layers=W["num_layers"],
+                                             mapping_type=W["mapping_type"], model_version=W["model_version"],
                                              lm_state_dict=lm_w).to(dev).train()
-    B = C2["batch_per_gpu"]
-    host = syn.make_caption_batch(B, C2["text_len"], C2["clip_dim"], C2["vocab"], seed=2021 + rank)
+    B = W["batch_per_gpu"]
+    host = syn.make_caption_batch(B, W["text_len"], W["clip_dim"], W["vocab"], seed=2021 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     opt = FlatAdamW(model, lr=1e-4)
+    from eavqa_b200.parallel import OverlappedGradReducer
+    # --overlap-allreduce: bucketed all-reduce on a communication stream, started per pair of mapper layers while the
+    # rest of the mapper backward runs.  Measured SLOWER at N = 2 (12.8 vs 11.25 ms/step): NCCL's CTAs occupy SMs for the
+    # whole collective and the persistent GEMMs (148 CTAs, static tile striding) then run their tiles in two waves.
+    # Default: one all-reduce of the whole flat buffer after the step.
+    reducer = OverlappedGradReducer(model) if (world > 1 and args.overlap_allreduce) else None
 
     def step(b):
         out = model(question_tokens=b["input_ids"], labels=b["labels"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"])
         out.loss.backward()
         g = model.last_flat_grads
-        if world > 1:
+        if reducer is not None:
+            reducer.reduce(g)
+        elif world > 1:
             dist.all_reduce(g)                               # sum; the 1/W of the DDP mean is folded into AdamW
         opt.step(g, grad_scale=1.0 / world)
         opt.zero_grad()
@@ -244,7 +268,7 @@ def main():
     lib.check(L.eavqa_profile_end(C.byref(tot_ms), C.byref(tot_fl), C.byref(nl), rep, len(rep)))
     gemm_ms, gemm_tf = tot_ms.value / prof_steps, tot_fl.value / prof_steps / 1e12
     achieved = gemm_tf / (gemm_ms * 1e-3)
-    step_tflops = GFLOP_PER_SAMPLE_C2 * B / 1e3 / (ms_step * 1e-3)
+    step_tflops = GFLOP_PER_SAMPLE[WORKLOAD] * B / 1e3 / (ms_step * 1e-3)
     # DRAM traffic of the GEMM launches: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 196 GEMM launches
     # of one step, per launch like `achieved` (profiles/r01_gemm_traffic_v13.json, made by tools/ncu_step_summary.py from
     # the committed launch list); algorithmic bytes per launch from the same per-launch records as the timings.
@@ -253,7 +277,7 @@ def main():
     alg_gb_per_launch = sum(alg) / 1e3 / max(nl.value, 1)
     traffic, traffic_note = None, "no ncu traffic summary under profiles/"
     tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic_v13.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and WORKLOAD == "c2":
         with open(tp) as f:
             t = json.load(f)
         traffic = t["gemm_dram_bytes_per_launch"] / 1e9
@@ -266,7 +290,7 @@ def main():
                 "peak_source": pk["source"], "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": gemm_tf,
                 "gemm_launches_per_step": nl.value // prof_steps, "gemm_share_of_step": gemm_ms / ms_step,
                 "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / pk["tflops"],
-                "algorithmic_gflop_per_sample": GFLOP_PER_SAMPLE_C2}
+                "algorithmic_gflop_per_sample": GFLOP_PER_SAMPLE[WORKLOAD]}
     if args.profile_report and rank == 0:
         with open(args.profile_report, "w") as f:
             f.write(rep.value.decode())
@@ -277,8 +301,12 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline}
 
     # ---- few-shot VQA answers/s (BASELINE configs[3]) and the CPU baseline: rank 0, N = 1 only ------------------------
-    del model, opt
+    if reducer is not None:
+        reducer.close()
+    del model, opt, reducer
     torch.cuda.empty_cache()
+    if WORKLOAD != "c2":
+        args.no_generate = args.no_cpu_baseline = True         # those legs belong to the metric's own configuration
     if world == 1 and not args.no_generate:
         line["few_shot_generate"] = bench_generate(dev, eavqa_b200, syn, args)
     if world == 1 and not args.no_cpu_baseline:

@@ -115,6 +115,32 @@ int eavqa_generate(eavqa_handle* h, int32_t batch, int32_t text_len, int32_t n_i
     API_END
 }
 
+int32_t eavqa_grad_bucket_count(const eavqa_handle* h) {
+    if (h == nullptr) return 0;
+    try {
+        return static_cast<int32_t>(h->engine->grad_buckets().size());
+    } catch (...) {
+        return 0;
+    }
+}
+
+int eavqa_grad_bucket_range(const eavqa_handle* h, int32_t index, int64_t* begin, int64_t* end) {
+    API_BEGIN
+    EAVQA_CHECK(h != nullptr && begin != nullptr && end != nullptr, "null argument");
+    const auto b = h->engine->grad_buckets();
+    EAVQA_CHECK(index >= 0 && index < static_cast<int32_t>(b.size()), "bucket index out of range");
+    *begin = b[index].first;
+    *end = b[index].second;
+    API_END
+}
+
+int eavqa_set_grad_events(eavqa_handle* h, void* const* events, int32_t n) {
+    API_BEGIN
+    EAVQA_CHECK(h != nullptr, "null handle");
+    h->engine->set_grad_events(events, n);
+    API_END
+}
+
 int eavqa_build_caption_labels(const int64_t* tokens, int32_t batch, int32_t text_len, int64_t pad_id, int64_t bos_id,
                                int64_t* labels, void* stream) {
     API_BEGIN

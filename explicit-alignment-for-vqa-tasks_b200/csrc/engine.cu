@@ -183,6 +183,43 @@ Engine::Engine(const eavqa_config& cfg) : cfg_(cfg) {
     side_enabled_ = !(e != nullptr && e[0] == '0');
     CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreateWithFlags(&join_event_, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&bucket_sync_event_, cudaEventDisableTiming));
+}
+
+std::vector<std::pair<int64_t, int64_t>> Engine::grad_buckets() const {
+    std::vector<std::pair<int64_t, int64_t>> out;
+    if (cfg_.mapper_type != EAVQA_MAPPER_TRANSFORMER) return out;
+    const int n = cfg_.mapper_layers;
+    auto layer_begin = [&](int l) { return pofs("transformer.layers." + std::to_string(l) + ".norm1.weight"); };
+    const int64_t layers_end = pofs("linear.weight");
+    for (int hi = n; hi > 0; hi -= 2) {                     // layers [lo, hi): the backward walks layers downwards
+        const int lo = std::max(0, hi - 2);
+        out.push_back(std::make_pair(layer_begin(lo), hi == n ? layers_end : layer_begin(hi)));
+    }
+    return out;
+}
+
+void Engine::set_grad_events(void* const* events, int n) {
+    grad_events_.clear();
+    if (events == nullptr || n == 0) return;
+    EAVQA_CHECK(n == static_cast<int>(grad_buckets().size()), "set_grad_events: one event per gradient bucket");
+    for (int i = 0; i < n; ++i) {
+        EAVQA_CHECK(events[i] != nullptr, "set_grad_events: null event");
+        grad_events_.push_back(static_cast<cudaEvent_t>(events[i]));
+    }
+}
+
+// every gradient of `bucket` has been enqueued (main stream: bias / LayerNorm grads; side stream: weight gradients):
+// the caller's event fires when both streams get there
+void Engine::bucket_done(int bucket, cudaStream_t main) {
+    if (grad_events_.empty()) return;
+    if (fork_used_ == 0) {                                  // nothing was forked (profiling / EAVQA_WGRAD_STREAM=0)
+        CUDA_CHECK(cudaEventRecord(grad_events_[bucket], main));
+        return;
+    }
+    CUDA_CHECK(cudaEventRecord(bucket_sync_event_, main));
+    CUDA_CHECK(cudaStreamWaitEvent(side_, bucket_sync_event_, 0));
+    CUDA_CHECK(cudaEventRecord(grad_events_[bucket], side_));
 }
 
 cudaStream_t Engine::fork(cudaStream_t main) {
@@ -210,6 +247,7 @@ Engine::~Engine() {
     if (side_) cudaStreamSynchronize(side_);
     for (cudaEvent_t ev : fork_events_) cudaEventDestroy(ev);
     if (join_event_) cudaEventDestroy(join_event_);
+    if (bucket_sync_event_) cudaEventDestroy(bucket_sync_event_);
     if (side_) cudaStreamDestroy(side_);
     for (void* p : owned_) cudaFree(p);
     if (host_flags_) cudaFreeHost(host_flags_);
@@ -505,6 +543,8 @@ void Engine::mapper_backward(const float* params, const MapperW& w, const Mapper
         gemm(dqkv[l], 3 * d, w.wqkv_t[l], 3 * d, M2, d, 3 * d, ep_bf16(dsmall, d), s);                    // da = dqkv [Wq;Wkv]
         layernorm_bwd(dsmall, d, f.x[2 * l], d, nullptr, params + pofs(p + "norm1.weight"), f.mean1[l], f.rstd1[l], dx, d, 1,
                       nullptr, 0, grads + pofs(p + "norm1.weight"), grads + pofs(p + "norm1.bias"), M2, d, 1e-5f, s);
+        // layers [l, l+2) (or the odd one at the top) are complete: their all-reduce may start (grad_buckets())
+        if ((n - l) % 2 == 0 || l == 0) bucket_done((n - l - 1) / 2, s);
     }
     // x0 = cat(linear(clip).view(N, cl, d), prefix_const)
     sum_over_batch_f32(dx + static_cast<size_t>(cl) * d, static_cast<int64_t>(S) * d, N, P_ * d, grads + pofs("prefix_const"), s);

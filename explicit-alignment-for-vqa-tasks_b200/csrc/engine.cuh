@@ -53,6 +53,12 @@ public:
     void finalize_lm(cudaStream_t s);
 
     const std::vector<TensorInfo>& mapper_tensors() const { return mapper_tensors_; }
+    // Gradient buckets for overlapping the data-parallel all-reduce with the mapper backward: contiguous ranges of the
+    // flat gradient buffer in the order in which the backward finishes them (transformer mapper: pairs of layers, last
+    // layers first; MLP mapper: none).  set_grad_events() installs one caller-owned cudaEvent_t per bucket; train_step
+    // records event k once every gradient of bucket k is final.
+    std::vector<std::pair<int64_t, int64_t>> grad_buckets() const;
+    void set_grad_events(void* const* events, int n);
     int64_t mapper_param_count() const { return mapper_count_; }
 
     void train_step(int B, int Tt, const float* clip, const int64_t* tokens, const int64_t* mask, const int64_t* labels,
@@ -95,6 +101,9 @@ private:
     std::vector<cudaEvent_t> fork_events_;
     size_t fork_used_ = 0;
     cudaEvent_t join_event_ = nullptr;
+    std::vector<cudaEvent_t> grad_events_;      // caller-owned, one per grad bucket (empty = not requested)
+    cudaEvent_t bucket_sync_event_ = nullptr;
+    void bucket_done(int bucket, cudaStream_t main);
     bool side_enabled_ = true;           // EAVQA_WGRAD_STREAM=0 serialises everything on the caller's stream (measurements)
     cudaStream_t fork(cudaStream_t main);   // side stream made to wait for everything enqueued on `main` so far
     void join(cudaStream_t main);           // `main` waits for the side stream

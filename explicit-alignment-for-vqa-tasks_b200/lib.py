@@ -42,6 +42,9 @@ PROTOTYPES = {
     "eavqa_generate": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                  c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_void_p, C.POINTER(c_int32),
                                  c_void_p]),
+    "eavqa_grad_bucket_count": (c_int32, [c_void_p]),
+    "eavqa_grad_bucket_range": (C.c_int, [c_void_p, c_int32, C.POINTER(c_int64), C.POINTER(c_int64)]),
+    "eavqa_set_grad_events": (C.c_int, [c_void_p, C.POINTER(c_void_p), c_int32]),
     "eavqa_build_caption_labels": (C.c_int, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
     "eavqa_ensemble_select": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),

@@ -49,3 +49,81 @@ def all_reduce_mean_(flat_grads: torch.Tensor) -> torch.Tensor:
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
         flat_grads.mul_(1.0 / w)
     return flat_grads
+
+
+def bucket_plan(n: int, buckets):
+    """Ranges of ``[0, n)`` to all-reduce: the engine's buckets in completion order, then whatever they leave uncovered
+    (ascending).  Pure host logic (tested on CPU)."""
+    buckets = [(int(b), int(e)) for b, e in buckets]
+    for b, e in buckets:
+        if not (0 <= b < e <= n):
+            raise ValueError("bucket [%d, %d) outside the gradient buffer of %d elements" % (b, e, n))
+    covered = sorted(buckets)
+    for (b0, e0), (b1, e1) in zip(covered, covered[1:]):
+        if b1 < e0:
+            raise ValueError("gradient buckets overlap")
+    rest, pos = [], 0
+    for b, e in covered:
+        if b > pos:
+            rest.append((pos, b))
+        pos = e
+    if pos < n:
+        rest.append((pos, n))
+    return buckets, rest
+
+
+class OverlappedGradReducer:
+    """All-reduce (sum) of the flat mapper gradient, bucket by bucket, overlapped with the mapper backward.
+
+    The engine records one CUDA event per bucket as soon as that bucket's gradients are final (``eavqa_set_grad_events``);
+    a communication stream waits on the event and runs the NCCL all-reduce of that range while the remaining layers'
+    backward is still executing.  The ranges the buckets do not cover (prefix_const, the input linear) are reduced after
+    the step.  ``reduce(grads)`` returns once the current stream is ordered after every all-reduce.
+
+    Use with a plain ``loss.backward()`` (upstream gradient 1): a loss scale would be applied to the buffer after the
+    buckets may already be in flight -- fold such factors into ``FlatAdamW.step(grad_scale=...)`` instead.
+    """
+
+    def __init__(self, model):
+        from . import lib as _lib
+        import ctypes as C
+        model._ensure_engine()
+        self.model = model
+        L = _lib.load()
+        h = model._handle
+        n = L.eavqa_grad_bucket_count(h)
+        ranges = []
+        for i in range(n):
+            b, e = C.c_int64(), C.c_int64()
+            _lib.check(L.eavqa_grad_bucket_range(h, i, C.byref(b), C.byref(e)))
+            ranges.append((b.value, e.value))
+        self.buckets, self.rest = bucket_plan(model._flat.numel(), ranges)
+        self.events = [torch.cuda.Event(enable_timing=False) for _ in self.buckets]
+        for ev in self.events:
+            ev.record()                                    # materialises the cudaEvent_t the engine will re-record
+        self.comm_stream = torch.cuda.Stream(device=model._flat.device)
+        if self.events:
+            arr = (C.c_void_p * len(self.events))(*[C.c_void_p(ev.cuda_event) for ev in self.events])
+            _lib.check(L.eavqa_set_grad_events(h, arr, len(self.events)))
+
+    def reduce(self, flat_grads: torch.Tensor) -> torch.Tensor:
+        if world() == 1:
+            return flat_grads
+        cur = torch.cuda.current_stream(flat_grads.device)
+        works = []
+        with torch.cuda.stream(self.comm_stream):
+            for (b, e), ev in zip(self.buckets, self.events):
+                self.comm_stream.wait_event(ev)
+                works.append(dist.all_reduce(flat_grads[b:e], op=dist.ReduceOp.SUM, async_op=True))
+        for (b, e) in self.rest:                           # final when the step's own stream gets here
+            works.append(dist.all_reduce(flat_grads[b:e], op=dist.ReduceOp.SUM, async_op=True))
+        for w in works:
+            w.wait()                                       # orders the current stream after the collective
+        flat_grads.record_stream(self.comm_stream)
+        cur.wait_stream(self.comm_stream)
+        return flat_grads
+
+    def close(self):
+        from . import lib as _lib
+        if self.model._handle is not None:
+            _lib.check(_lib.load().eavqa_set_grad_events(self.model._handle, None, 0))

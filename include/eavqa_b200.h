@@ -106,6 +106,17 @@ int eavqa_splice(int32_t batch, int32_t text_len, int32_t n_images, int32_t pref
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t eavqa_launch_count(void);
 
+/* Overlapping the data-parallel gradient exchange (Lightning DDP's bucketed all-reduce, main.py:138) with the mapper
+ * backward.  The engine reports contiguous ranges [begin, end) of the flat gradient buffer in the order in which
+ * eavqa_train_step finishes them (transformer mapper: pairs of layers, last layers first; MLP mapper: none).  The caller
+ * installs one cudaEvent_t per range (it keeps owning them); every later eavqa_train_step records event k, on an internal
+ * stream, once all gradients of range k are final, so a communication stream can wait on it and all-reduce that range
+ * while the rest of the backward still runs.  Gradients outside the ranges are final when eavqa_train_step's work on
+ * `stream` completes.  n = 0 uninstalls. */
+int32_t eavqa_grad_bucket_count(const eavqa_handle* h);
+int eavqa_grad_bucket_range(const eavqa_handle* h, int32_t index, int64_t* begin, int64_t* end);
+int eavqa_set_grad_events(eavqa_handle* h, void* const* events, int32_t n);
+
 /* ---- the steps right around the path inside the reference's executors ---- */
 /* ClipCapExecutor.training_step label construction (clipcap_exector.py:134-150), replacing its Python double loop over
  * [B, T] tensor elements: labels = input_ids with pads -> -100, everything up to and including <BOS> -> -100, and the

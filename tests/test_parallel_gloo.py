@@ -67,3 +67,19 @@ def test_shard_batch_rejects_ragged_split():
     from eavqa_b200 import parallel
     with pytest.raises(ValueError):
         parallel.shard_batch({"x": torch.zeros(5, 2)}, 0, 2)
+
+
+def test_bucket_plan_orders_engine_buckets_first_and_covers_the_rest():
+    import pytest
+    from eavqa_b200 import parallel
+    # transformer mapper layout: [prefix_const | layer 0..3 | linear]; engine buckets arrive last layers first
+    n = 100
+    buckets, rest = parallel.bucket_plan(n, [(50, 90), (10, 50)])
+    assert buckets == [(50, 90), (10, 50)] and rest == [(0, 10), (90, 100)]
+    covered = sorted(buckets + rest)
+    assert covered[0][0] == 0 and covered[-1][1] == n and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    assert parallel.bucket_plan(8, []) == ([], [(0, 8)])
+    with pytest.raises(ValueError):
+        parallel.bucket_plan(10, [(0, 6), (5, 10)])
+    with pytest.raises(ValueError):
+        parallel.bucket_plan(10, [(4, 12)])
