@@ -159,6 +159,20 @@ int eavqa_ensemble_select(const float* logprob, const int64_t* tokens, int32_t n
     API_END
 }
 
+int eavqa_rices_search(const float* queries, const float* database, int64_t n_queries, int64_t n_database, int32_t dim, int32_t k,
+                       float* out_scores, int64_t* out_index, void* stream) {
+    API_BEGIN
+    rices_search(queries, database, n_queries, n_database, dim, k, out_scores, out_index, S(stream));
+    API_END
+}
+
+int eavqa_rices_rerank(const float* query, const float* table, int64_t n_queries, int32_t dim, const int32_t* candidates,
+                       int32_t n_candidates, float* out_sim, int32_t* out_pos, void* stream) {
+    API_BEGIN
+    rices_rerank(query, table, n_queries, dim, candidates, n_candidates, out_sim, out_pos, S(stream));
+    API_END
+}
+
 int eavqa_scale_grads(float* grads, int64_t n, const float* scale, void* stream) {
     API_BEGIN
     EAVQA_CHECK(grads && scale && n > 0, "bad argument");

@@ -103,6 +103,15 @@ void ensemble_select(const float* logprob, const int64_t* tokens, int E, int B, 
 // x[0..n) *= *scale (device scalar); no memory traffic when *scale == 1
 void scale_by_device_scalar(float* x, int64_t n, const float* scale, cudaStream_t s);
 
+// ---------------------------------------------------------------- RICES retrieval (rices.cu)
+// faiss.normalize_L2 + IndexFlatIP.search (get_question_knn.py:64-76): queries [M, D], database [N, D] fp32;
+// out_scores [M, k] fp32 descending, out_index [M, k] int64 (ties: lower index first; fewer than k rows: -FLT_MAX / -1)
+void rices_search(const float* queries, const float* database, int64_t M, int64_t N, int D, int k, float* out_scores,
+                  int64_t* out_index, cudaStream_t s);
+// per-question re-ranking of candidate rows of `table` (get_image_knn_from_text_knn.py:79-92): cand [M, C] int32, -1 = padding
+void rices_rerank(const float* query, const float* table, int64_t M, int D, const int* cand, int C, float* out_sim, int* out_pos,
+                  cudaStream_t s);
+
 // ---------------------------------------------------------------- optimiser (elementwise.cu)
 // torch.optim.AdamW semantics on the flat mapper buffer (clipcap_exector.py:79-81): decoupled weight decay,
 // bias correction; g = grads * grad_scale

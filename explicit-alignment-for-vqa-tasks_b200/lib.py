@@ -48,6 +48,8 @@ PROTOTYPES = {
     "eavqa_build_caption_labels": (C.c_int, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
     "eavqa_ensemble_select": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
+    "eavqa_rices_search": (C.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "eavqa_rices_rerank": (C.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "eavqa_scale_grads": (C.c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "eavqa_splice": (C.c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_int64,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

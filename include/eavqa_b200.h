@@ -133,6 +133,22 @@ int eavqa_ensemble_select(const float* logprob, const int64_t* tokens, int32_t n
                           const int64_t* skip_ids, int32_t n_skip, float* scores, int32_t* best, int64_t* best_tokens,
                           void* stream);
 
+/* RICES in-context example retrieval, the step before the few-shot path.
+ * eavqa_rices_search replaces faiss.normalize_L2 + faiss.IndexFlatIP (GPU) .search(k) of
+ * src/in_context_example_selection/get_question_knn.py:64-76: queries [n_queries, dim] and database [n_database, dim] are
+ * fp32 device arrays (not modified; normalisation happens on packed copies); out_scores [n_queries, k] fp32 in descending
+ * order, out_index [n_queries, k] int64 database rows (equal scores: lower row first; when n_database < k the tail is
+ * -FLT_MAX / -1 as in faiss).  dim % 8 == 0, k <= 2048 (faiss' GPU limit too).  Scores are tensor-core inner products of
+ * hi/lo-split bf16 operands with fp32 accumulation (error < 2e-5).  Synchronises `stream` before returning.
+ * eavqa_rices_rerank replaces the per-question index of get_image_knn_from_text_knn.py:79-92: for question q the
+ * candidates are rows candidates[q, 0..n_candidates) of `table` [*, dim] (-1 = padding); out_sim / out_pos
+ * [n_queries, n_candidates]: cosine similarities in descending order and the candidate POSITIONS (faiss' I for the
+ * per-question index); padding comes last as -FLT_MAX / -1.  n_candidates <= 4096. */
+int eavqa_rices_search(const float* queries, const float* database, int64_t n_queries, int64_t n_database, int32_t dim, int32_t k,
+                       float* out_scores, int64_t* out_index, void* stream);
+int eavqa_rices_rerank(const float* query, const float* table, int64_t n_queries, int32_t dim, const int32_t* candidates,
+                       int32_t n_candidates, float* out_sim, int32_t* out_pos, void* stream);
+
 /* grads[0..n) *= *scale (device fp32 scalar: the upstream gradient autograd hands to backward()); skips the pass when
  * *scale == 1 without a host sync.  n % 4 == 0. */
 int eavqa_scale_grads(float* grads, int64_t n, const float* scale, void* stream);

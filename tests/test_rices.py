@@ -1,0 +1,142 @@
+"""RICES retrieval: normalised inner-product top-k (faiss IndexFlatIP semantics) and the per-question
+candidate re-ranking.  CPU: the oracle against brute force.  GPU: the kernels through the C ABI against the oracle.
+
+Floating point: scores within 3e-5 (hi/lo-split bf16 tensor-core products, fp32 accumulation; the north star states no
+tolerance for this row, faiss itself computes in fp32); indices exact wherever the oracle's neighbouring scores are more
+than that apart, and always consistent with the returned scores."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rices as orc
+
+TOL = 3e-5
+
+
+# ------------------------------------------------------------------------------------------------ CPU: oracle
+def test_oracle_known_answers():
+    db = np.array([[1, 0], [0, 2], [1, 1], [0, 0], [-1, 0]], dtype=np.float32)
+    q = np.array([[2, 0], [1, 1]], dtype=np.float32)
+    D, I = orc.knn_inner_product(q, db, 3)
+    assert I.tolist() == [[0, 2, 1], [2, 0, 1]]
+    assert np.allclose(D[0], [1.0, 2 ** -0.5, 0.0], atol=1e-7) and np.allclose(D[1], [1.0, 2 ** -0.5, 2 ** -0.5], atol=1e-7)
+    D, I = orc.knn_inner_product(q, db[:2], 4)                     # fewer rows than k: faiss pads with -FLT_MAX / -1
+    assert I[0].tolist() == [0, 1, -1, -1] and D[0, 2] == -float(orc.FLT_MAX)
+    assert np.array_equal(orc.normalize_l2(np.zeros((1, 4), np.float32)), np.zeros((1, 4), np.float32))
+
+
+def test_oracle_against_brute_force():
+    g = np.random.default_rng(0)
+    q, db = g.standard_normal((7, 16)).astype(np.float32), g.standard_normal((50, 16)).astype(np.float32)
+    db[10] = db[3]                                                 # an exact duplicate: ties go to the lower row
+    D, I = orc.knn_inner_product(q, db, 50)
+    for m in range(7):
+        s = [float(np.dot(q[m] / np.linalg.norm(q[m]), db[n] / np.linalg.norm(db[n]))) for n in range(50)]
+        want = sorted(range(50), key=lambda n: (-s[n], n))
+        got = I[m].tolist()
+        assert got.index(3) + 1 == got.index(10)
+        assert all(abs(s[a] - s[b]) < 1e-6 for a, b in zip(got, want))
+    cand = np.array([[3, 10, -1, 7], [-1, -1, -1, -1]])
+    sims, pos = orc.rerank_candidates(q[:2], db, cand)
+    assert sorted(pos[0, :3].tolist()) == [0, 1, 3] and pos[0, 3] == -1 and (pos[1] == -1).all()
+    assert sims[0, 0] >= sims[0, 1] >= sims[0, 2]
+
+
+# ------------------------------------------------------------------------------------------------ GPU: kernels vs oracle
+def _check_search(q, db, k):
+    from eavqa_b200.rices import knn_inner_product
+    D, I = knn_inner_product(torch.from_numpy(q).cuda(), torch.from_numpy(db).cuda(), k)
+    D, I = D.cpu().numpy().astype(np.float64), I.cpu().numpy()
+    Dr, Ir = orc.knn_inner_product(q, db, k)
+    n_real = min(k, db.shape[0])
+    assert np.abs(D[:, :n_real] - Dr[:, :n_real]).max() < TOL                      # the sorted score lists agree
+    assert (I[:, n_real:] == -1).all() and (D[:, n_real:] == -float(orc.FLT_MAX)).all()
+    assert (np.diff(D[:, :n_real], axis=1) <= 0).all()                              # descending
+    qn, dn = orc.normalize_l2(q).astype(np.float64), orc.normalize_l2(db).astype(np.float64)
+    for m in range(q.shape[0]):
+        got = I[m, :n_real]
+        assert len(set(got.tolist())) == n_real and got.min() >= 0 and got.max() < db.shape[0]
+        true = dn[got] @ qn[m]
+        assert np.abs(true - D[m, :n_real]).max() < TOL                             # every index carries its own score
+        # positions whose oracle neighbours are further than the tolerance away are decided: indices must match there
+        s = Dr[m, :n_real]
+        gap_prev = np.concatenate(([np.inf], s[:-1] - s[1:]))
+        gap_next = np.concatenate((s[:-1] - s[1:], [np.inf]))
+        if n_real == k and k < db.shape[0]:
+            full = np.sort(dn @ qn[m])[::-1]
+            gap_next[-1] = s[-1] - full[k]                                          # the boundary to rank k + 1
+        sure = (gap_prev > 2 * TOL) & (gap_next > 2 * TOL)
+        assert (got[sure] == Ir[m, :n_real][sure]).all()
+    return D, I
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,D,k", [(37, 1000, 64, 1), (37, 1000, 64, 5), (5, 300, 8, 300), (3, 40, 16, 64), (1100, 5000, 32, 16),
+                                     (16, 20000, 768, 100)])
+def test_rices_search_matches_oracle(M, N, D, k):
+    g = np.random.default_rng(M * 1000 + k)
+    q, db = g.standard_normal((M, D)).astype(np.float32), (g.standard_normal((N, D)) * 3).astype(np.float32)
+    _check_search(q, db, k)
+
+
+@pytest.mark.gpu
+def test_rices_search_full_k_over_several_chunks_with_clustered_scores():
+    """k = 2048 (the reference's value) over 40 000 database rows = three 16 384-row chunks; CLIP-like data: a shared
+    component makes all cosine similarities large and close together."""
+    g = np.random.default_rng(7)
+    base = g.standard_normal((1, 768)).astype(np.float32)
+    q = (base + 0.5 * g.standard_normal((24, 768))).astype(np.float32)
+    db = (base + 0.5 * g.standard_normal((40000, 768))).astype(np.float32)
+    D, I = _check_search(q, db, 2048)
+    assert D.min() > 0.5
+
+
+@pytest.mark.gpu
+def test_rices_search_ties_and_zero_rows():
+    g = np.random.default_rng(3)
+    db = g.standard_normal((600, 32)).astype(np.float32)
+    db[100:110] = db[5]                    # duplicated questions are common in VQA: equal scores, lower row first
+    db[300] = 0                            # a zero row stays zero (score 0)
+    q = np.concatenate((db[5:6] * 2.5, g.standard_normal((3, 32)).astype(np.float32), np.zeros((1, 32), np.float32)))
+    D, I = _check_search(q, db, 32)
+    assert I[0, :11].tolist() == [5] + list(range(100, 110))
+    assert (D[4] == 0).all() and I[4].tolist() == list(range(32))      # all-zero query: every score 0, rows in order
+
+
+@pytest.mark.gpu
+def test_rices_search_rejects_bad_arguments():
+    from eavqa_b200 import lib
+    from eavqa_b200.rices import knn_inner_product
+    x = torch.zeros(4, 16, device="cuda")
+    with pytest.raises(lib.EavqaError):
+        knn_inner_product(x, x, 4096)                                   # k > 2048
+    with pytest.raises(lib.EavqaError):
+        knn_inner_product(torch.zeros(4, 12, device="cuda"), torch.zeros(9, 12, device="cuda"), 2)     # D % 8 != 0
+    with pytest.raises(lib.EavqaError):
+        knn_inner_product(torch.zeros(4, 16), torch.zeros(9, 16), 2)    # CPU tensors: no fallback
+
+
+@pytest.mark.gpu
+def test_rices_rerank_matches_oracle():
+    from eavqa_b200.rices import rerank_candidates
+    g = np.random.default_rng(11)
+    table = g.standard_normal((5000, 768)).astype(np.float32)
+    q = g.standard_normal((20, 768)).astype(np.float32)
+    cand = g.integers(0, 5000, (20, 300)).astype(np.int32)
+    cand[:, 250:] = -1
+    cand[3, 10:] = -1
+    cand[7] = -1
+    sims, pos = rerank_candidates(torch.from_numpy(q).cuda(), torch.from_numpy(table).cuda(), torch.from_numpy(cand).cuda())
+    sims, pos = sims.cpu().numpy().astype(np.float64), pos.cpu().numpy()
+    sr, pr = orc.rerank_candidates(q, table, cand)
+    valid = pr >= 0
+    assert ((pos >= 0) == valid).all()
+    assert np.abs(sims[valid] - sr[valid]).max() < 1e-5 and (sims[~valid] == -float(orc.FLT_MAX)).all()
+    for m in range(20):
+        n = int(valid[m].sum())
+        if n == 0:
+            continue
+        s = sr[m, :n]
+        sure = (np.concatenate(([np.inf], s[:-1] - s[1:])) > 1e-5) & (np.concatenate((s[:-1] - s[1:], [np.inf])) > 1e-5)
+        assert (pos[m, :n][sure] == pr[m, :n][sure]).all()
+        assert sorted(pos[m, :n].tolist()) == sorted(pr[m, :n].tolist())
