@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-generate", action="store_true", help="skip the few-shot answers/s leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rices", action="store_true", help="skip the RICES retrieval leg (SURVEY.md 8f row 4)")
     ap.add_argument("--profile-report", default="", help="write the per-shape GEMM timing report to this file")
     ap.add_argument("--only-timed", action="store_true", help="run only warm-up + the timed region (for ncu launch lists)")
     ap.add_argument("--overlap-allreduce", action="store_true",
@@ -306,9 +307,11 @@ def main():
     del model, opt, reducer
     torch.cuda.empty_cache()
     if WORKLOAD != "c2":
-        args.no_generate = args.no_cpu_baseline = True         # those legs belong to the metric's own configuration
+        args.no_generate = args.no_cpu_baseline = args.no_rices = True         # those legs belong to the metric's own configuration
     if world == 1 and not args.no_generate:
         line["few_shot_generate"] = bench_generate(dev, eavqa_b200, syn, args)
+    if world == 1 and not args.no_rices:
+        line["rices_retrieval"] = bench_rices(with_cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(steps=6, warmup=2)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -354,6 +357,27 @@ def bench_generate(dev, eavqa_b200, syn, args):
                                    "KV-cached greedy decode, host tensors in / token tensor out", "prompt_len": T0,
                        "tokens_out_shape": list(out.shape)},
             "algorithmic_gflop_per_answer": 82.8, "tflops": 82.8 * c["batch"] / 1e3 / (ms * 1e-3)}
+
+
+def bench_rices(with_cpu=True):
+    """RICES in-context example retrieval (the step before the few-shot path): faiss.normalize_L2 + IndexFlatIP.search
+    (k = 2048) over a VQA2-train-sized database of CLIP text embeddings, 4096 queries per call."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import rices_bench
+    r = rices_bench.run(M=4096, N=443757, D=768, k=2048, reps=3)
+    if with_cpu:
+        import numpy as np
+        from oracle import rices as orc
+        g = np.random.default_rng(0)
+        base = g.standard_normal((1, 768)).astype(np.float32)
+        db = (base + 0.5 * g.standard_normal((443757, 768))).astype(np.float32)
+        q = (base + 0.5 * g.standard_normal((32, 768))).astype(np.float32)
+        t0 = time.perf_counter()
+        orc.knn_inner_product(q, db, 2048)
+        sec = time.perf_counter() - t0
+        r["cpu_port"] = {"value": 32 / sec, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "32 queries against the same database (numpy float64, oracle/rices.py; includes normalising the database)"}
+    return r
 
 
 if __name__ == "__main__":

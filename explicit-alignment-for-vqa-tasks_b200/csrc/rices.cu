@@ -110,11 +110,12 @@ __global__ void __launch_bounds__(256) rices_select_kernel(const float* __restri
     pdl_wait();
     extern __shared__ __align__(8) uint8_t smem_sel[];
     Cand* pool = reinterpret_cast<Cand*>(smem_sel);
-    __shared__ int s_cnt;
+    __shared__ int s_cnt, s_batch;
     const int row = blockIdx.x;
     const int P = next_pow2(cap);
     int cnt = pool_n[row];
     float thr = pool_thr[row];
+    if (threadIdx.x == 0) s_batch = 0;
     for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
         pool[t].s = pool_s[static_cast<int64_t>(row) * cap + t];
         pool[t].i = pool_i[static_cast<int64_t>(row) * cap + t];
@@ -122,28 +123,49 @@ __global__ void __launch_bounds__(256) rices_select_kernel(const float* __restri
     if (threadIdx.x == 0) s_cnt = cnt;
     __syncthreads();
     const float* srow = S + static_cast<int64_t>(row) * ldS;
-    for (int c0 = 0; c0 < ncols; c0 += blockDim.x) {
-        if (cnt + static_cast<int>(blockDim.x) > cap) {          // room for a whole batch, or compact first (CTA-uniform)
-            compact_pool(pool, cnt, k, thr, P);
+    // batches of 4 columns per thread (ldS and the row base are 16-byte aligned).  After the first chunks hardly anything
+    // beats the threshold: a batch nobody passes costs one barrier and no shared-memory traffic.
+    const int batch = 4 * blockDim.x;
+    for (int c0 = 0; c0 < ncols; c0 += batch) {
+        const int c = c0 + 4 * threadIdx.x;
+        float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (c + 3 < ncols) {
+            v = *reinterpret_cast<const float4*>(srow + c);
+        } else if (c < ncols) {
+            v.x = srow[c];
+            if (c + 1 < ncols) v.y = srow[c + 1];
+            if (c + 2 < ncols) v.z = srow[c + 2];
+        }
+        // how many elements of this batch beat the threshold (exact count: compaction only when the pool would overflow;
+        // the first version compacted whenever a full batch might not fit, i.e. on almost every batch -> 235 us per chunk)
+        int mine = (v.x > thr) + (v.y > thr) + (v.z > thr) + (v.w > thr);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine > 0) atomicAdd(&s_batch, mine);
+        __syncthreads();
+        const int total = s_batch;                                  // CTA-uniform
+        if (total == 0) continue;
+        if (cnt + total > cap) {
+            compact_pool(pool, cnt, k, thr, P);                     // raises thr: fewer than `total` may pass now, never more
             if (threadIdx.x == 0) s_cnt = cnt;
             __syncthreads();
         }
-        const int c = c0 + threadIdx.x;
-        if (c < ncols) {
-            const float v = srow[c];
-            if (v > thr) {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (e[j] > thr) {
                 const int pos = atomicAdd(&s_cnt, 1);
-                pool[pos].s = v;
-                pool[pos].i = static_cast<int>(col0 + c);
+                pool[pos].s = e[j];
+                pool[pos].i = static_cast<int>(col0 + c + j);
             }
-        }
         __syncthreads();
         cnt = s_cnt;
-        __syncthreads();                                        // everyone has read the count before the next batch bumps it
+        if (threadIdx.x == 0) s_batch = 0;
+        __syncthreads();                                            // count read / batch counter reset before the next batch
     }
-    // leave at most k candidates and an exact threshold for the next chunk
-    if (cnt > k) compact_pool(pool, cnt, k, thr, P);
-    else if (cnt == k && thr == -INFINITY) compact_pool(pool, cnt, k, thr, P);
+    // The pool goes back unsorted with up to `cap` entries and the threshold of the LAST compaction: a stale (lower)
+    // threshold only admits a few extra candidates, whereas compacting at the end of every chunk cost one 4096-element
+    // sort per query per chunk (~2/3 of the selection time).  rices_finalize_kernel does the final sort.
     for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
         pool_s[static_cast<int64_t>(row) * cap + t] = pool[t].s;
         pool_i[static_cast<int64_t>(row) * cap + t] = pool[t].i;
@@ -235,16 +257,27 @@ __global__ void __launch_bounds__(256) rices_rerank_kernel(const float* __restri
     (void)n_valid;
 }
 
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    explicit DevBuf(size_t n) { CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * std::max<size_t>(n, 1))); }
-    ~DevBuf() { cudaFree(p); }
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-};
+int select_cap(int k) { return k + std::max(k, 1024); }      // the pool always has room for one 1024-column batch beyond k
 
-int select_cap(int k) { return k + std::max(k, 256); }
+// workspace kept between calls (grow-only): the index build of a 444k x 768 database needs 2 GB, and cudaMalloc / cudaFree
+// of that size cost more than the search of a thousand queries
+struct Workspace {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~Workspace() { if (p) cudaFree(p); }
+    uint8_t* reserve(size_t bytes, cudaStream_t s) {
+        if (bytes > cap) {
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            if (p) CUDA_CHECK(cudaFree(p));
+            p = nullptr; cap = 0;
+            CUDA_CHECK(cudaMalloc(&p, bytes));
+            cap = bytes;
+        }
+        return static_cast<uint8_t*>(p);
+    }
+};
+Workspace g_ws;
+size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
 
 }  // namespace
 
@@ -268,9 +301,17 @@ void rices_search(const float* queries, const float* database, int64_t M, int64_
     const int64_t Mc = std::min<int64_t>(M, 1024);
     const int64_t Nc = std::min<int64_t>(N, 16384);
     const int64_t ldS = (Nc + 3) / 4 * 4;
-    DevBuf<bf16> db(static_cast<size_t>(N) * K3), q(static_cast<size_t>(Mc) * K3);
-    DevBuf<float> S(static_cast<size_t>(Mc) * ldS), pool_s(static_cast<size_t>(Mc) * cap), pool_thr(static_cast<size_t>(Mc));
-    DevBuf<int> pool_i(static_cast<size_t>(Mc) * cap), pool_n(static_cast<size_t>(Mc));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += align256(bytes); return o; };
+    const size_t o_db = take(sizeof(bf16) * static_cast<size_t>(N) * K3), o_q = take(sizeof(bf16) * static_cast<size_t>(Mc) * K3);
+    const size_t o_S = take(sizeof(float) * static_cast<size_t>(Mc) * ldS), o_ps = take(sizeof(float) * static_cast<size_t>(Mc) * cap);
+    const size_t o_pi = take(sizeof(int) * static_cast<size_t>(Mc) * cap), o_pn = take(sizeof(int) * static_cast<size_t>(Mc));
+    const size_t o_pt = take(sizeof(float) * static_cast<size_t>(Mc));
+    uint8_t* base = g_ws.reserve(off, s);
+    struct { bf16* p; } db{reinterpret_cast<bf16*>(base + o_db)}, q{reinterpret_cast<bf16*>(base + o_q)};
+    struct { float* p; } S{reinterpret_cast<float*>(base + o_S)}, pool_s{reinterpret_cast<float*>(base + o_ps)},
+        pool_thr{reinterpret_cast<float*>(base + o_pt)};
+    struct { int* p; } pool_i{reinterpret_cast<int*>(base + o_pi)}, pool_n{reinterpret_cast<int*>(base + o_pn)};
     launch_kernel(rices_normalize_split_kernel, dim3(static_cast<unsigned>(ceil_div64(N, 8))), dim3(256), 0, s, database, N, D, db.p, 1);
     KERNEL_CHECK();
     count_launch();
@@ -300,7 +341,7 @@ void rices_search(const float* queries, const float* database, int64_t M, int64_
         KERNEL_CHECK();
         count_launch();
     }
-    CUDA_CHECK(cudaStreamSynchronize(s));       // workspace is freed on return
+    CUDA_CHECK(cudaStreamSynchronize(s));       // the cached workspace may be reused by the next call on any stream
 }
 
 // query [M, D], table [n_table, D] fp32; cand [M, C] int32 rows of `table` (-1 = padding); out_sim [M, C], out_pos [M, C] int32
