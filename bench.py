@@ -249,7 +249,7 @@ def main():
     def e2e_step():
         b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         loss = step(b)
-        return float(loss)                                   # D2H of the step's result
+        return float(loss.detach())                          # D2H of the step's result
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)

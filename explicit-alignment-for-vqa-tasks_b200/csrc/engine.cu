@@ -727,7 +727,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
 
     MapperW mw;
     MapperFwd mf;
-    float *prefix = nullptr, *h0 = nullptr, *h1 = nullptr, *h2 = nullptr, *logits = nullptr, *x_a = nullptr, *x_b = nullptr, *x_c = nullptr;
+    float *prefix = nullptr, *h0 = nullptr, *h1 = nullptr, *h2 = nullptr, *logits = nullptr, *x_a = nullptr;
     int *plan = nullptr, *valid0 = nullptr, *validD = nullptr, *row_index = nullptr, *unfinished = nullptr, *flags = nullptr;
     bf16 *u = nullptr, *qkv = nullptr, *att = nullptr, *fc_act = nullptr, *hc = nullptr, *kv = nullptr;
     float *mean = nullptr, *rstd = nullptr, *part_val = nullptr;
@@ -746,7 +746,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         mean = a.get<float>(m); rstd = a.get<float>(m);
         row_index = a.get<int>(B); hc = a.get<bf16>(static_cast<size_t>(B) * d);
         logits = a.get<float>(static_cast<size_t>(B) * Vpad_);
-        x_a = a.get<float>(static_cast<size_t>(B) * d); x_b = a.get<float>(static_cast<size_t>(B) * d); x_c = a.get<float>(static_cast<size_t>(B) * d);
+        x_a = a.get<float>(static_cast<size_t>(B) * d);          // fp32 residual rows of the single-token steps
         unfinished = a.get<int>(B); flags = a.get<int>(max_new + 1);
         part_val = a.get<float>(static_cast<size_t>(B) * kGreedySplitMax); part_idx = a.get<int>(static_cast<size_t>(B) * kGreedySplitMax);
         arrivals = a.get<unsigned>(B);
@@ -819,7 +819,6 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     //      step, clipcap.py:416-419; same function, 11x less work).  M = B rows per GEMM: every projection is split along K
     //      over all SMs into fp32 accumulators; bias / residual / LayerNorm / gelu live in the small kernels between them,
     //      each of which also zeroes the accumulator of the GEMM that follows.  x_a is the fp32 residual row.
-    (void)x_b; (void)x_c;
     for (int step = 1; step < max_new; ++step) {
         const int pos = T0 + step - 1;
         decode_residual_ln(x_a, nullptr, nullptr, layers_[0].ln1_g, layers_[0].ln1_b, u, B, d, 1e-5f, acc_qkv, 3 * d, s);

@@ -78,9 +78,6 @@ private:
                         cudaStream_t s);
     void mapper_backward(const float* params, const MapperW& w, const MapperFwd& f, const float* dprefix,
                          int64_t dprefix_batch_stride, int N, float* grads, cudaStream_t s);
-    void lm_block_forward(int l, int M, int B, int T, const float* h_in, float* h_mid, float* h_out, const int* valid,
-                          bf16* u, bf16* qkv, bf16* att, float* lse, float* mean1, float* rstd1, float* mean2, float* rstd2,
-                          bf16* fc_pre, bf16* fc_act, cudaStream_t s);
 
     eavqa_config cfg_;
     int d_, L_, H_, V_, Vpad_, P_, S_, D_;
