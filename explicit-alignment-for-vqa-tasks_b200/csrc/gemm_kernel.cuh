@@ -58,6 +58,11 @@ constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int CHUNK = 32;     // accumulator columns per epilogue step
 constexpr int EPI_BUF = 4096; // one staging tile: 32 rows x 128 B
+constexpr int CLC_STAGES = 6; // in-flight "next work item" responses (producer <= MMA + 1 tile <= epilogue + 3 tiles)
+// offsets inside the barrier block (1024-B aligned): pipeline barriers first (<= 208 B), then the CLC ring
+constexpr int CLC_RESP_OFS = 208;                          // CLC_STAGES x 16 B responses
+constexpr int CLC_FULL_OFS = CLC_RESP_OFS + 16 * CLC_STAGES;
+constexpr int CLC_EMPTY_OFS = CLC_FULL_OFS + 8 * CLC_STAGES;
 
 template <int MODE>
 struct Epi {
@@ -83,8 +88,9 @@ struct Cfg {
     static constexpr int HALF = BN / 2;              // columns per epilogue warp
     static constexpr int NCHUNK = HALF / CHUNK;
     static constexpr int EPI_SMEM = EPI_WARPS * 2 * EPI_BUF;     // per warp: bufA (out) + bufB (in / out2)
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int BAR_BYTES = 512;
     static constexpr int SMEM = STAGES * (STAGE_A + STAGE_B) + EPI_SMEM + BAR_BYTES + 1024;
+    static_assert(16 * STAGES + 32 + 8 * EPI_WARPS + 4 <= CLC_RESP_OFS && CLC_EMPTY_OFS + 8 * CLC_STAGES <= BAR_BYTES, "barrier block layout");
     static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "UMMA N / epilogue split");
     static_assert(STAGE_B % 1024 == 0, "B stage must keep 1024-B alignment");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -129,12 +135,51 @@ struct TmaMaps {
     CUtensorMap a, b, out, out2, in;
 };
 
+// Dynamic persistent scheduling (cluster launch control, ptx.cuh).  The grid has one CTA (pair) per work item; a CTA starts
+// with its own block index and then keeps asking the hardware for the index of a CTA that has not been launched yet.
+// The producer thread issues one query per work item it starts (so the answer is there long before anyone needs it);
+// every role thread / epilogue warp reads the same sequence of answers from a ring in shared memory.
+struct WorkFeed {
+    uint32_t resp, full, empty;     // shared addresses of the ring (responses, full / empty barriers)
+    int slot = 0;
+    uint32_t phase = 0;
+    bool pair;                      // CTA pair: answers are multicast to both CTAs, `empty` lives in the leader
+    __device__ __forceinline__ WorkFeed(uint32_t bars, bool pair_) : resp(bars + CLC_RESP_OFS), full(bars + CLC_FULL_OFS),
+                                                                     empty(bars + CLC_EMPTY_OFS), pair(pair_) {}
+    __device__ __forceinline__ void advance() {
+        if (++slot == CLC_STAGES) { slot = 0; phase ^= 1; }
+    }
+    // producer side: request the next work item (leader only talks to the hardware; every CTA arms its own barrier)
+    __device__ __forceinline__ void request(bool leader) {
+        if (leader) ptx::mbar_wait(empty + 8 * slot, phase ^ 1);          // every reader is done with this slot's last answer
+        ptx::mbar_arrive_expect_tx(full + 8 * slot, 16);
+        if (leader) {
+            if (pair) ptx::clc_try_cancel_multicast(resp + 16 * slot, full + 8 * slot);
+            else ptx::clc_try_cancel(resp + 16 * slot, full + 8 * slot);
+        }
+        advance();
+    }
+    // consumer side: block index of the next work item's first CTA, or -1 when the grid is exhausted.
+    // `arrive` = this thread reports the slot as read (one thread per role / epilogue warp).
+    __device__ __forceinline__ int next(bool arrive) {
+        ptx::mbar_wait(full + 8 * slot, phase);
+        const int id = ptx::clc_decode(resp + 16 * slot);
+        ptx::fence_proxy_async_smem();                                     // generic read before the async proxy rewrites the slot
+        if (arrive) {
+            if (pair) ptx::mbar_arrive_cluster(empty + 8 * slot, 0);
+            else ptx::mbar_arrive(empty + 8 * slot);
+        }
+        advance();
+        return id;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // epilogue role (8 warps), shared by the 1-CTA and the 2-CTA (cta_group::2) kernels
 // ---------------------------------------------------------------------------------------------
 template <int BN, int MODE, class Coords, class Release>
-__device__ __forceinline__ void epilogue_role(const TmaMaps& maps, const GemmEpilogue& ep, int M, int N, int num_n, int num_tiles,
-                                              int tile_begin, int tile_step, Coords coords, Release release_tmem,
+__device__ __forceinline__ void epilogue_role(const TmaMaps& maps, const GemmEpilogue& ep, int M, int N, int num_n, int first_tile,
+                                              uint32_t bars, bool pair, Coords coords, Release release_tmem,
                                               uint32_t tmem_base, uint32_t tfull_bar, uint32_t smem_epi, uint32_t in_bar0,
                                               int warp, int lane) {
     using C = Cfg<BN>;
@@ -161,24 +206,18 @@ __device__ __forceinline__ void epilogue_role(const TmaMaps& maps, const GemmEpi
         ptx::mbar_arrive_expect_tx(in_bar, in_bytes);
         ptx::tma_load_2d(bufB, &maps.in, in_bar, n_idx * BN + half * C::HALF + c * CHUNK, m_idx * BM + quarter * 32);
     };
-    auto next_tile_with_work = [&](int tile) {
-        int t = tile;
-        while (t < num_tiles) {
-            int m_idx, n_idx;
-            coords(t, m_idx, n_idx);
-            if (n_valid_chunks(n_idx) > 0) break;
-            t += tile_step;
-        }
-        return t;
+    // the operand of a tile's first chunk is requested when the tile becomes known (below, at the end of the previous tile)
+    auto prefetch_in = [&](int tile) {            // lane 0 only
+        int m_idx, n_idx;
+        coords(tile, m_idx, n_idx);
+        if (n_valid_chunks(n_idx) > 0) issue_in(tile, 0);
     };
-    if (E::has_in && lane == 0) {
-        const int t0 = next_tile_with_work(tile_begin);
-        if (t0 < num_tiles) issue_in(t0, 0);
-    }
+    if (E::has_in && lane == 0) prefetch_in(first_tile);
+    WorkFeed feed(bars, pair);
 
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
+    for (int tile = first_tile;;) {
         int m_idx, n_idx;
         coords(tile, m_idx, n_idx);
         const int row0 = m_idx * BM + quarter * 32;
@@ -347,14 +386,7 @@ __device__ __forceinline__ void epilogue_role(const TmaMaps& maps, const GemmEpi
                     }
                 }
                 __syncwarp();                     // every lane has consumed bufB: fetch the next chunk's operand
-                if (lane == 0) {
-                    if (c + 1 < nvalid) {
-                        issue_in(tile, c + 1);
-                    } else {
-                        const int tn = next_tile_with_work(tile + tile_step);
-                        if (tn < num_tiles) issue_in(tn, 0);
-                    }
-                }
+                if (lane == 0 && c + 1 < nvalid) issue_in(tile, c + 1);
             }
             const bool store_out = !E::ce || ep.out != nullptr;      // loss-only evaluation keeps no logits
             if (ep.debug != 3 && store_out) {
@@ -397,6 +429,11 @@ __device__ __forceinline__ void epilogue_role(const TmaMaps& maps, const GemmEpi
             ep.ce_partial[static_cast<size_t>(row) * ep.ce_tiles + n_idx * 2 + half] = make_float2(ce_m, ce_s);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+        // next work item (every lane reads the same answer; lane 0 reports the slot as read)
+        const int id = feed.next(lane == 0);
+        if (id < 0) break;
+        tile = pair ? (id >> 1) : id;
+        if (E::has_in && lane == 0) prefetch_in(tile);
     }
     if (lane == 0) tma_store_wait_read<0>();      // staging smem must outlive the last bulk stores
 }
@@ -445,6 +482,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
             ptx::mbar_init(tempty_bar + 8 * i, EPI_WARPS);     // one arrive per epilogue warp
         }
         for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(in_bar0 + 8 * i, 1);
+        for (int i = 0; i < CLC_STAGES; ++i) {
+            ptx::mbar_init(bars + CLC_FULL_OFS + 8 * i, 1);
+            ptx::mbar_init(bars + CLC_EMPTY_OFS + 8 * i, 2 + EPI_WARPS);       // producer + MMA + epilogue warps
+        }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async_smem();
     }
@@ -460,10 +501,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
     const int num_m = (M + BM - 1) / BM;
     const int num_n = (N + BN - 1) / BN;
     const int split = ep.split_k > 1 ? ep.split_k : 1;      // split-K: `split` consecutive work items share an output tile
-    const int num_tiles = num_m * num_n * split;
     const int num_kb = (K + BK - 1) / BK;
-    const int tile_begin = blockIdx.x;
-    const int tile_step = gridDim.x;
+    const int first_tile = blockIdx.x;                      // the grid has one CTA per work item (see WorkFeed)
     auto coords = [&](int tile, int& m_idx, int& n_idx) { tile_coords(tile / split, num_m, num_n, m_idx, n_idx); };
     auto kb_range = [&](int tile, int& kb0, int& kb1) {     // balanced, never empty (split <= num_kb)
         const int sp = tile % split;
@@ -477,7 +516,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
             pdl_wait();       // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
+            WorkFeed req(bars, false), feed(bars, false);
+            for (int tile = first_tile; tile >= 0; tile = feed.next(true)) {
+                req.request(true);                                        // ask for the work item after this one
                 int m_idx, n_idx, kb0, kb1;
                 coords(tile, m_idx, n_idx);
                 kb_range(tile, kb0, kb1);
@@ -510,7 +551,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
+            WorkFeed feed(bars, false);
+            for (int tile = first_tile; tile >= 0; tile = feed.next(true)) {
                 ptx::mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);     // epilogue drained this buffer
                 ptx::tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
@@ -539,7 +581,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int K, c
         }
     } else {
         // ===================== epilogue warps =====================
-        epilogue_role<BN, MODE>(maps, ep, M, N, num_n, num_tiles, tile_begin, tile_step, coords,
+        epilogue_role<BN, MODE>(maps, ep, M, N, num_n, first_tile, bars, false, coords,
                                 [&](int acc) { ptx::mbar_arrive(tempty_bar + 8 * acc); }, tmem_base, tfull_bar, smem_epi, in_bar0,
                                 warp, lane);
     }
@@ -566,8 +608,9 @@ struct Cfg2 {
     static constexpr int STAGES = (BN == 256) ? 5 : (BN == 192) ? 5 : 6;
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     static constexpr int EPI_SMEM = EPI_WARPS * 2 * EPI_BUF;
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int BAR_BYTES = 512;
     static constexpr int SMEM = STAGES * (STAGE_A + STAGE_B) + EPI_SMEM + BAR_BYTES + 1024;
+    static_assert(16 * STAGES + 32 + 8 * EPI_WARPS + 4 <= CLC_RESP_OFS, "barrier block layout");
     static_assert(BN == 128 || BN == 192 || BN == 256, "pair tile width");
     static_assert(STAGE_B % 1024 == 0, "B stage must keep 1024-B alignment");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -613,6 +656,10 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int
             ptx::mbar_init(tempty_bar + 8 * i, 2 * EPI_WARPS);
         }
         for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(in_bar0 + 8 * i, 1);
+        for (int i = 0; i < CLC_STAGES; ++i) {
+            ptx::mbar_init(bars + CLC_FULL_OFS + 8 * i, 1);
+            ptx::mbar_init(bars + CLC_EMPTY_OFS + 8 * i, 3 + 2 * EPI_WARPS);   // leader's: 2 producers + 1 MMA + 2 x 8 epilogue warps
+        }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async_smem();
     }
@@ -629,10 +676,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int
     const int num_m = (M + BM - 1) / BM;
     const int num_n = (N + BN - 1) / BN;
     const int num_pm = (num_m + 1) / 2;                   // pair tiles along M (256 rows)
-    const int num_tiles = num_pm * num_n;
     const int num_kb = (K + BK - 1) / BK;
-    const int tile_begin = blockIdx.x / 2;
-    const int tile_step = gridDim.x / 2;
+    const int first_tile = blockIdx.x / 2;                // the grid has one CTA pair per tile (see WorkFeed)
     auto coords = [&](int tile, int& m_idx, int& n_idx) {
         int pm, pn;
         tile_coords(tile, num_pm, num_n, pm, pn);
@@ -646,7 +691,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int
             pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
+            WorkFeed req(bars, true), feed(bars, true);
+            for (int tile = first_tile, id = 0; id >= 0; id = feed.next(true), tile = id >> 1) {
+                req.request(leader);                                      // the leader asks; both CTAs receive the answer
                 int m_idx, n_idx;
                 coords(tile, m_idx, n_idx);
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -667,7 +714,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
+            WorkFeed feed(bars, true);
+            for (int id = 0; id >= 0; id = feed.next(true)) {             // the MMA loop does not need the tile coordinates
                 ptx::mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);     // both CTAs' epilogues drained this buffer
                 ptx::tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
@@ -689,7 +737,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ TmaMaps maps, int M, int N, int
         }
     } else {
         // ===================== epilogue warps (both CTAs, own 128 rows) =====================
-        epilogue_role<BN, MODE>(maps, ep, M, N, num_n, num_tiles, tile_begin, tile_step, coords,
+        epilogue_role<BN, MODE>(maps, ep, M, N, num_n, first_tile, bars, true, coords,
                                 [&](int acc) { ptx::mbar_arrive_cluster(tempty_bar + 8 * acc, 0); }, tmem_base, tfull_bar, smem_epi,
                                 in_bar0, warp, lane);
     }
@@ -755,8 +803,7 @@ void launch_1cta(const GemmArgs& a, cudaStream_t stream) {
     }
     fill_epi_maps(a, Epi<MODE>::out_f32, maps);
     const int split = a.ep.split_k > 1 ? a.ep.split_k : 1;
-    const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN) * split;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
+    const int grid = ceil_div(a.M, BM) * ceil_div(a.N, BN) * split;      // one CTA per work item; running CTAs cancel + adopt the rest
     void* token = nullptr;
     gemm_prof_before(stream, a, BN, &token);
     launch_with_attrs(gemm_bf16_tn_kernel<BN, MODE, MN>, grid, C::SMEM, 1, stream, maps, a);
@@ -775,9 +822,7 @@ void launch_2cta(const GemmArgs& a, cudaStream_t stream) {
     maps.a = gemm_make_map(a.A, a.M, a.K, a.lda, BM, MAP_OPERAND);
     maps.b = gemm_make_map(a.B, a.N, a.K, a.ldb, BN / 2, MAP_OPERAND);      // each CTA of the pair stages half of the B tile
     fill_epi_maps(a, Epi<MODE>::out_f32, maps);
-    const int tiles = ceil_div(ceil_div(a.M, BM), 2) * ceil_div(a.N, BN);
-    const int max_clusters = num_sms() / 2;
-    const int grid = (tiles < max_clusters ? tiles : max_clusters) * 2;
+    const int grid = 2 * ceil_div(ceil_div(a.M, BM), 2) * ceil_div(a.N, BN);      // one CTA pair per 256 x BN tile
     void* token = nullptr;
     gemm_prof_before(stream, a, BN + 1000, &token);
     launch_with_attrs(gemm_bf16_tn_2cta_kernel<BN, MODE>, grid, C::SMEM, 2, stream, maps, a);

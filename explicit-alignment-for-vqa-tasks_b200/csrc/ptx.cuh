@@ -171,6 +171,34 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
         ::"r"(bar), "r"(rank) : "memory");
 }
 
+// ------------------------------------------------------------------ cluster launch control (dynamic persistent scheduling)
+// A running CTA (cluster) asks the hardware to CANCEL a not-yet-launched CTA (cluster) of its own grid and takes over its
+// block index.  The grid is launched with one CTA (pair) per work item; the CTAs that get an SM first drain the rest,
+// so a kernel adapts to however many SMs are free (other streams, NCCL) instead of assuming all 148.  The 16-byte
+// response lands in shared memory and completes 16 tx-bytes on an mbarrier.
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp_smem, uint32_t bar) {
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                 ::"r"(resp_smem), "r"(bar) : "memory");
+}
+// cluster form: the response and the tx-bytes are delivered at the same shared offsets in EVERY CTA of the cluster
+__device__ __forceinline__ void clc_try_cancel_multicast(uint32_t resp_smem, uint32_t bar) {
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+                 ::"r"(resp_smem), "r"(bar) : "memory");
+}
+// blockIdx.x of the first CTA of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_decode(uint32_t resp_smem) {
+    uint32_t x, valid;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b128 r;\n\t"
+        "ld.shared.b128 r, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, r;\n\t"
+        "selp.u32 %1, 1, 0, p;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "@p clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %0, r;\n\t}"
+        : "=r"(x), "=r"(valid) : "r"(resp_smem) : "memory");
+    return valid ? static_cast<int>(x) : -1;
+}
+
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor for a K-major bf16 operand tile laid out by TMA with
 // SWIZZLE_128B and a 64-element (128-byte) inner box: rows are 128 B apart, 8-row groups

@@ -107,7 +107,7 @@ class OverlappedGradReducer:
             _lib.check(L.eavqa_set_grad_events(h, arr, len(self.events)))
 
     def reduce(self, flat_grads: torch.Tensor) -> torch.Tensor:
-        if world() == 1:
+        if not (dist.is_available() and dist.is_initialized()):
             return flat_grads
         cur = torch.cuda.current_stream(flat_grads.device)
         works = []

@@ -299,3 +299,42 @@ def test_full_size_few_shot_generation_rows_are_independent():
     again = m.generate(question_tokens=b["input_ids"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"], **kw).cpu()
     assert torch.equal(full, again)              # deterministic
     assert int(full.min()) >= 0 and int(full.max()) < cfg_lm["vocab"]
+
+
+def test_overlapped_grad_reducer_on_a_one_rank_nccl_group():
+    """The bucketed all-reduce path (engine-recorded events, communication stream, NCCL) on a world of one: the buckets and
+    the rest tile the flat gradient buffer, the reduced gradients equal the plain ones, and uninstalling the events restores
+    the plain step.  (The 2-rank equivalence is checked by tools/check_overlap_allreduce.py under torchrun.)"""
+    import socket
+    import torch.distributed as dist
+    from eavqa_b200.parallel import OverlappedGradReducer
+    case = CASES["train_tiny_transformer"]
+    lm_w, mapper_w, batch, cfg = build_case(case)
+    model = build_model(case, lm_w, mapper_w)
+    kw = dict(question_tokens=batch["input_ids"], labels=batch["labels"], prefix=batch["clip_embeddings"],
+              question_mask=batch["attention_mask"])
+    model(**kw).loss.backward()
+    plain = model.last_flat_grads.clone()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, world_size=1, rank=0, device_id=torch.device("cuda", 0))
+    try:
+        red = OverlappedGradReducer(model)
+        n = plain.numel()
+        spans = sorted(red.buckets + red.rest)
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert len(red.buckets) == (case["num_layers"] + 1) // 2
+        for _ in range(2):
+            model.zero_grad(set_to_none=True)
+            model(**kw).loss.backward()
+            got = red.reduce(model.last_flat_grads)
+            torch.cuda.synchronize()
+            assert float((got.double() - plain.double()).norm() / plain.double().norm()) < 1e-5
+        red.close()
+        model.zero_grad(set_to_none=True)
+        model(**kw).loss.backward()
+        assert float((model.last_flat_grads.double() - plain.double()).norm() / plain.double().norm()) < 1e-5
+    finally:
+        dist.destroy_process_group()
