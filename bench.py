@@ -148,8 +148,8 @@ def main():
     ap.add_argument("--no-rices", action="store_true", help="skip the RICES retrieval leg (SURVEY.md 8f row 4)")
     ap.add_argument("--profile-report", default="", help="write the per-shape GEMM timing report to this file")
     ap.add_argument("--only-timed", action="store_true", help="run only warm-up + the timed region (for ncu launch lists)")
-    ap.add_argument("--no-overlap-allreduce", action="store_true",
-                    help="N > 1: one all-reduce of the whole flat gradient after the step instead of the bucketed, overlapped one")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="N > 1: bucketed gradient all-reduce overlapped with the mapper backward instead of one all-reduce after the step")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2 = BASELINE configs[1] (the metric's configuration, default); c5 = configs[4], GPT-2 XL, 64 samples / GPU")
     args = ap.parse_args()
@@ -191,10 +191,11 @@ def main():
     resident = {k: v.to(dev) for k, v in host.items()}
     opt = FlatAdamW(model, lr=1e-4)
     from eavqa_b200.parallel import OverlappedGradReducer
-    # N > 1: bucketed all-reduce on a communication stream, started per pair of mapper layers while the rest of the mapper
-    # backward runs (N = 2: 11.20 vs 11.34 ms/step for one all-reduce after the step; with the GEMMs' former static tile
-    # striding it was 12.80 ms, because NCCL's CTAs hold SMs for the whole collective -- cluster launch control fixed that).
-    reducer = OverlappedGradReducer(model) if (world > 1 and not args.no_overlap_allreduce) else None
+    # --overlap-allreduce: bucketed all-reduce on a communication stream, started per pair of mapper layers while the rest of
+    # the mapper backward runs.  Measured (profiles/README.md): N = 2 11.20 vs 11.34 ms/step for one all-reduce after the
+    # step, N = 8 11.50 vs 11.26 ms/step (NVLS makes the 167 MB all-reduce cost only ~0.4 ms; NCCL's CTAs slow the GEMMs they
+    # overlap by about as much).  Default: one all-reduce of the whole flat buffer after the step.
+    reducer = OverlappedGradReducer(model) if (world > 1 and args.overlap_allreduce) else None
 
     def step(b):
         out = model(question_tokens=b["input_ids"], labels=b["labels"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"])
