@@ -187,9 +187,9 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------ single-token decode glue
 // Decode steps run their M = batch-row GEMMs split along K over all SMs, accumulating fp32 partials into scratch rows
-// (profiles/: unsplit, the projections used 16 of 148 SMs and took 16-20 us each).  These two kernels are what sits
-// between those GEMMs: they apply bias / residual / LayerNorm / gelu to the accumulated rows and zero the scratch rows
-// of the NEXT GEMM.  One 128-thread CTA per row.
+// (profiles/: unsplit, the projections used 16 of 148 SMs and took 16-20 us each).  This kernel is what sits between
+// those GEMMs: it applies bias / residual / LayerNorm to the accumulated rows and zeroes the scratch rows of the NEXT
+// split-K GEMM.  One 128-thread CTA per row.
 __device__ __forceinline__ float block_sum_128(float v, float* red) {
     v = warp_sum(v);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -247,28 +247,6 @@ __global__ void __launch_bounds__(128) decode_residual_ln_kernel(float* __restri
             o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
             up[c] = o;
         }
-    }
-    if (zero != nullptr) {
-        float4* zp = reinterpret_cast<float4*>(zero + static_cast<size_t>(row) * zero_n);
-        for (int c = threadIdx.x; c < (zero_n >> 2); c += 128) zp[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-
-// out[row] = gelu_new(acc[row] + bias) (bf16, n columns); zero[row, 0..zero_n) = 0
-__global__ void __launch_bounds__(128) decode_bias_gelu_kernel(const float* __restrict__ acc, const float* __restrict__ bias,
-                                                               bf16* __restrict__ out, int n, float* __restrict__ zero, int zero_n) {
-    pdl_trigger();
-    pdl_wait();
-    const int row = blockIdx.x;
-    const float4* ap = reinterpret_cast<const float4*>(acc + static_cast<size_t>(row) * n);
-    uint2* op = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * n);
-    for (int c = threadIdx.x; c < (n >> 2); c += 128) {
-        const float4 a = ap[c];
-        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c);
-        uint2 o;
-        o.x = pack_bf16x2(gelu_new(a.x + b.x), gelu_new(a.y + b.y));
-        o.y = pack_bf16x2(gelu_new(a.z + b.z), gelu_new(a.w + b.w));
-        op[c] = o;
     }
     if (zero != nullptr) {
         float4* zp = reinterpret_cast<float4*>(zero + static_cast<size_t>(row) * zero_n);
@@ -1037,13 +1015,6 @@ void decode_residual_ln(float* x, const float* acc, const float* bias, const flo
     KERNEL_CHECK();
     count_launch();
 }
-void decode_bias_gelu(const float* acc, const float* bias, bf16* out, int rows, int n, float* zero, int zero_n, cudaStream_t s) {
-    EAVQA_CHECK(n % 4 == 0 && zero_n % 4 == 0, "decode_bias_gelu: widths must be multiples of 4");
-    launch_kernel(decode_bias_gelu_kernel, dim3(rows), dim3(128), 0, s, acc, bias, out, n, zero, zero_n);
-    KERNEL_CHECK();
-    count_launch();
-}
-
 template <int MAXV>
 static void launch_ln_bwd(const bf16* dy, int ld_dy, const float* x, int ld_x, const int* row_index, const float* gamma,
                           const float* mean, const float* rstd, float* dx, int ld_dx, int accumulate, bf16* dx_bf16,

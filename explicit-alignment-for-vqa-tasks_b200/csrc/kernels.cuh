@@ -57,8 +57,6 @@ void layernorm_param_grads(const bf16* dy, int ld_dy, const float* x, int ld_x, 
 // x[row] += acc[row] + bias (acc, bias may both be null); u[row] = LN(x[row]) (bf16); zero[row, 0..zero_n) = 0 (may be null)
 void decode_residual_ln(float* x, const float* acc, const float* bias, const float* gamma, const float* beta, bf16* u, int rows, int d,
                         float eps, float* zero, int zero_n, cudaStream_t s);
-// out[row] = gelu_new(acc[row] + bias) (bf16 [rows, n]); zero[row, 0..zero_n) = 0 (may be null)
-void decode_bias_gelu(const float* acc, const float* bias, bf16* out, int rows, int n, float* zero, int zero_n, cudaStream_t s);
 
 // ---------------------------------------------------------------- embedding / splice (elementwise.cu)
 // plan[b, t] >= 0 : token id ; < 0 : -(prefix_row + 1) ; valid[b, t] = key-validity (attention mask)
