@@ -100,9 +100,11 @@ __device__ __forceinline__ void warp_gemm_nt(float (&acc)[8][4], const uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------ forward
+// kv_cache != null (generation prefill): the CTA of the LAST query block walks every key block anyway and copies the K / V
+// tiles it has in shared memory into the head-major KV cache (K block [B, H, Tmax, 64], then V) -- no separate fill kernel.
 __global__ void __launch_bounds__(128, 4) lm_attention_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
                                                                bf16* __restrict__ o, float* __restrict__ lse, int T,
-                                                               int H) {
+                                                               int H, bf16* __restrict__ kv_cache, int Tmax) {
     pdl_trigger();
     pdl_wait();
     __shared__ __align__(16) bf16 Qs[BLK * LDS];
@@ -147,6 +149,20 @@ __global__ void __launch_bounds__(128, 4) lm_attention_fwd_kernel(const bf16* __
             __syncthreads();
         }
 
+        if (kv_cache != nullptr && qb == static_cast<int>(gridDim.x) - 1) {
+            const int nb = gridDim.z;
+            bf16* kc = kv_cache + (static_cast<int64_t>(b) * H + h) * Tmax * HD;
+            bf16* vc = kc + static_cast<int64_t>(nb) * H * Tmax * HD;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = tid + 128 * i;
+                const int r = idx >> 3, c = (idx & 7) * 8;
+                if (k0 + r < T) {
+                    *reinterpret_cast<uint4*>(kc + static_cast<int64_t>(k0 + r) * HD + c) = *reinterpret_cast<const uint4*>(Ks + r * LDS + c);
+                    *reinterpret_cast<uint4*>(vc + static_cast<int64_t>(k0 + r) * HD + c) = *reinterpret_cast<const uint4*>(Vs + r * LDS + c);
+                }
+            }
+        }
         float sacc[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -580,23 +596,7 @@ __global__ void __launch_bounds__(128, 4) lm_attention_bwd_single_kernel(const b
 // ------------------------------------------------------------------------------------------ KV cache / decode
 // KV cache of one layer: K block [B, H, Tmax, 64] followed by the V block of the same shape (bf16).  Head-major: the
 // keys / values one (sample, head) attends over are contiguous (Tmax * 128 B), so a decode step streams them with
-// fully coalesced loads and DRAM-page locality (token-major [B, Tmax, 2d] rows cost 29 us per layer for 78 MB).
-__global__ void kv_cache_fill_kernel(const uint4* __restrict__ qkv, uint4* __restrict__ cache, int B, int T, int Tmax,
-                                     int H) {
-    pdl_trigger();
-    pdl_wait();
-    const int d8 = H * 8;                                     // uint4 (8 bf16) per d-wide row; 8 per head
-    const int64_t total = static_cast<int64_t>(B) * T * 2 * d8;
-    const int64_t vofs = static_cast<int64_t>(B) * H * Tmax * 8;
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % (2 * d8));         // 0 .. d8-1: k, d8 .. 2 d8-1: v
-        const int64_t row = i / (2 * d8);
-        const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
-        const int which = c >= d8, cc = c - which * d8, h = cc >> 3, e = cc & 7;
-        cache[which * vofs + ((static_cast<int64_t>(b) * H + h) * Tmax + t) * 8 + e] = qkv[row * 3 * d8 + d8 + c];
-    }
-}
+// fully coalesced loads.  Prefill fills it from inside lm_attention_fwd_kernel; each decode step appends one position.
 
 // Split-K decode path: q | k | v arrive as fp32 GEMM accumulators + bias.  One 128-thread CTA per (sample, head); its four
 // warps each take a quarter of the keys (flash-decoding style: per-warp max / sum / partial P.V, merged through shared
@@ -1107,9 +1107,10 @@ __global__ void __launch_bounds__(128) mapper_attention_bwd_kernel(const bf16* _
 }  // namespace
 
 // ============================================================================================ launchers
-void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, int B, int T, int H, cudaStream_t s) {
+void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, int B, int T, int H, cudaStream_t s, bf16* kv_cache,
+                      int Tmax) {
     dim3 grid(ceil_div(T, BLK), H, B);
-    launch_kernel(lm_attention_fwd_kernel, dim3(grid), dim3(128), 0, s, qkv, valid, o, lse, T, H);
+    launch_kernel(lm_attention_fwd_kernel, dim3(grid), dim3(128), 0, s, qkv, valid, o, lse, T, H, kv_cache, Tmax);
     KERNEL_CHECK();
     count_launch();
 }
@@ -1140,15 +1141,6 @@ void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf
     count_launch();
 }
 
-void kv_cache_fill(const bf16* qkv, bf16* cache, int B, int T, int Tmax, int d, cudaStream_t s) {
-    EAVQA_CHECK(d % HD == 0, "kv_cache_fill: d must be a multiple of the head size");
-    const int64_t total = static_cast<int64_t>(B) * T * 2 * (d / 8);
-    const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), static_cast<int64_t>(num_sms()) * 8));
-    launch_kernel(kv_cache_fill_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const uint4*>(qkv), reinterpret_cast<uint4*>(cache), B, T,
-                  Tmax, d / HD);
-    KERNEL_CHECK();
-    count_launch();
-}
 void lm_attention_decode_acc(const float* qkv_acc, const float* qkv_bias, bf16* cache, const int* valid, int valid_stride, bf16* o,
                              float* zero, int B, int H, int pos, int Tmax, cudaStream_t s) {
     const size_t smem = sizeof(float) * Tmax;

@@ -572,8 +572,7 @@ static void lm_block(const LmLayer& w, int d, int H, const LmBlockIO& io, cudaSt
     // HF modeling_gpt2.py:262-309
     layernorm_fwd(io.h_in, d, nullptr, w.ln1_g, w.ln1_b, io.u, d, io.mean1, io.rstd1, M, d, 1e-5f, s);
     gemm(io.u, d, w.w_qkv_t, d, M, 3 * d, d, ep_bf16(io.qkv, 3 * d, w.b_qkv), s);
-    if (io.kv_cache != nullptr) kv_cache_fill(io.qkv, io.kv_cache, io.B, io.T, io.Tmax, d, s);     // prefill
-    lm_attention_fwd(io.qkv, io.valid, io.att, io.lse, io.B, io.T, H, s);
+    lm_attention_fwd(io.qkv, io.valid, io.att, io.lse, io.B, io.T, H, s, io.kv_cache, io.Tmax);      // prefill also fills the KV cache
     gemm(io.att, d, w.w_o_t, d, M, d, d, ep_f32(io.h_mid, d, w.b_o, io.h_in, d), s);
     layernorm_fwd(io.h_mid, d, nullptr, w.ln2_g, w.ln2_b, io.u, d, io.mean2, io.rstd2, M, d, 1e-5f, s);
     GemmEpilogue e = ep_bf16(io.fc_act, 4 * d, w.b_fc);

@@ -119,12 +119,13 @@ void adamw_step(float* params, const float* grads, float* m, float* v, int64_t n
 // ---------------------------------------------------------------- attention (attention.cu)
 // GPT-2 causal attention with key-padding mask, head_dim 64, qkv [B*T, 3d] bf16 (q | k | v, heads contiguous).
 // o [B*T, d] bf16; lse [B, H, T] fp32 (of scaled scores).
-void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, int B, int T, int H, cudaStream_t s);
+// kv_cache != null (generation prefill): also writes every K / V row into the head-major KV cache of this layer
+void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, int B, int T, int H, cudaStream_t s,
+                      bf16* kv_cache = nullptr, int Tmax = 0);
 // dqkv [B*T, 3d] bf16; dq_scratch fp32 [B*T, d] (only touched when T > 64)
 void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf16* d_o, const float* lse, bf16* dqkv,
                       float* dq_scratch, int B, int T, int H, cudaStream_t s);
 // KV cache per layer: K block [B, H, Tmax, 64] then V block [B, H, Tmax, 64] (bf16, head-major)
-void kv_cache_fill(const bf16* qkv, bf16* cache, int B, int T, int Tmax, int d, cudaStream_t s);
 // one new query per (b, h): q | k | v given as fp32 GEMM accumulators [B, 3d] + bias [3d] (split-K decode path); appends this
 // step's k, v at position pos and attends over keys [0, pos] where valid; four warps per (sample, head) share the keys;
 // also zeroes zero[b, h*64 .. h*64+64) (the next GEMM's accumulator rows, [B, d])
