@@ -271,13 +271,13 @@ def main():
     achieved = gemm_tf / (gemm_ms * 1e-3)
     step_tflops = GFLOP_PER_SAMPLE[WORKLOAD] * B / 1e3 / (ms_step * 1e-3)
     # DRAM traffic of the GEMM launches: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 196 GEMM launches
-    # of one step, per launch like `achieved` (profiles/r01_gemm_traffic_v13.json, made by tools/ncu_step_summary.py from
+    # of one step, per launch like `achieved` (profiles/r01_gemm_traffic_v24.json, made by tools/ncu_step_summary.py from
     # the committed launch list); algorithmic bytes per launch from the same per-launch records as the timings.
     import re
     alg = [float(m.group(2)) * int(m.group(1)) for m in re.finditer(r"launches=(\d+) .*alg_mbytes=([0-9.]+)", rep.value.decode())]
     alg_gb_per_launch = sum(alg) / 1e3 / max(nl.value, 1)
     traffic, traffic_note = None, "no ncu traffic summary under profiles/"
-    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic_v13.json")
+    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic_v24.json")
     if os.path.exists(tp) and WORKLOAD == "c2":
         with open(tp) as f:
             t = json.load(f)

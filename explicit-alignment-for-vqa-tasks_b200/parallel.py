@@ -124,6 +124,14 @@ class OverlappedGradReducer:
         return flat_grads
 
     def close(self):
+        """Uninstall the events from the engine (it only borrows them: they must outlive their installation)."""
         from . import lib as _lib
-        if self.model._handle is not None:
+        if self.events and self.model._handle is not None:
             _lib.check(_lib.load().eavqa_set_grad_events(self.model._handle, None, 0))
+        self.events = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
