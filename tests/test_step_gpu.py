@@ -338,3 +338,30 @@ def test_overlapped_grad_reducer_on_a_one_rank_nccl_group():
         assert float((model.last_flat_grads.double() - plain.double()).norm() / plain.double().norm()) < 1e-5
     finally:
         dist.destroy_process_group()
+
+
+def test_decode_attention_long_history_crosses_the_staging_limit():
+    """Greedy decoding whose KV history grows from 218 to 231 keys: the first steps use the decode-attention kernel that
+    stages the whole history in shared memory (<= 224 keys), the later ones the direct-load kernel.  Tiny sharpened LM,
+    compared with the live oracle (no KV cache there: the whole sequence is re-run every step)."""
+    from oracle.cases import _case
+    case = _case("generate", "gpt2-tiny", "mlp", 3, 214, 64, 4, 4, 2, ragged=True, hot_rows=64, max_length=14, n_positions=256)
+    lm_w, mapper_w, batch, cfg = build_case(case)
+    model = build_model(case, lm_w, mapper_w).eval()
+    kw = dict(max_length=case["max_length"], pad_token_id=case["pad_token_id"], eos_token_id=None)
+    got, top = model.generate(question_tokens=batch["input_ids"], prefix=batch["clip_embeddings"],
+                              question_mask=batch["attention_mask"], return_top_logits=True, **kw)
+    ref, margins = orc.generate(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"], batch["attention_mask"],
+                                return_margins=True, **kw)
+    assert batch["input_ids"].shape[1] + case["prefix_length"] == 218
+    checked, longest = 0, 0
+    for g, r, mg in zip(got, ref, margins):
+        n = len(r)
+        for i, m in enumerate(mg):
+            if float(m) < 0.05:          # beyond a near-tie the two decodes legitimately follow different prefixes
+                n = i
+                break
+        assert g[:n] == r[:n], (g, r)
+        checked += n
+        longest = max(longest, n)
+    assert checked >= 24 and longest >= 10      # the comparison reaches past the 224-key switch (decode step 7)
