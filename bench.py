@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--only-timed", action="store_true", help="run only warm-up + the timed region (for ncu launch lists)")
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="N > 1: bucketed gradient all-reduce overlapped with the mapper backward instead of one all-reduce after the step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the headline): 256 samples per GPU; strong: 256 samples in total, 256 / N per GPU (SURVEY.md 8d)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2 = BASELINE configs[1] (the metric's configuration, default); c5 = configs[4], GPT-2 XL, 64 samples / GPU")
     args = ap.parse_args()
@@ -168,9 +170,18 @@ def main():
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version line to STDOUT, next to the JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version line to STDOUT when the first communicator is created: keep stdout for the JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     import eavqa_b200
     import eavqa_b200.synthetic as syn
@@ -186,6 +197,9 @@ def main():
                                              mapping_type=W["mapping_type"], model_version=W["model_version"],
                                              lm_state_dict=lm_w).to(dev).train()
     B = W["batch_per_gpu"]
+    if args.scaling == "strong":
+        assert B % world == 0, "strong scaling needs the global batch to divide by the number of GPUs"
+        B = B // world
     host = syn.make_caption_batch(B, W["text_len"], W["clip_dim"], W["vocab"], seed=2021 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
@@ -297,8 +311,9 @@ def main():
             f.write(rep.value.decode())
 
     line = {"metric": "mapper_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": dict(workload_config(world), batch_per_gpu=B, global_batch=B * world),
+            "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline}
 
     # ---- few-shot VQA answers/s (BASELINE configs[3]) and the CPU baseline: rank 0, N = 1 only ------------------------
