@@ -102,6 +102,7 @@ __device__ __forceinline__ void warp_gemm_nt(float (&acc)[8][4], const uint32_t 
 // ------------------------------------------------------------------------------------------ forward
 // kv_cache != null (generation prefill): the CTA of the LAST query block walks every key block anyway and copies the K / V
 // tiles it has in shared memory into the head-major KV cache (K block [B, H, Tmax, 64], then V) -- no separate fill kernel.
+template <bool WRITE_KV>
 __global__ void __launch_bounds__(128, 4) lm_attention_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
                                                                bf16* __restrict__ o, float* __restrict__ lse, int T,
                                                                int H, bf16* __restrict__ kv_cache, int Tmax) {
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(128, 4) lm_attention_fwd_kernel(const bf16* __
             __syncthreads();
         }
 
-        if (kv_cache != nullptr && qb == static_cast<int>(gridDim.x) - 1) {
+        if (WRITE_KV && qb == static_cast<int>(gridDim.x) - 1) {
             const int nb = gridDim.z;
             bf16* kc = kv_cache + (static_cast<int64_t>(b) * H + h) * Tmax * HD;
             bf16* vc = kc + static_cast<int64_t>(nb) * H * Tmax * HD;
@@ -1245,7 +1246,8 @@ __global__ void __launch_bounds__(128) mapper_attention_bwd_kernel(const bf16* _
 void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, int B, int T, int H, cudaStream_t s, bf16* kv_cache,
                       int Tmax) {
     dim3 grid(ceil_div(T, BLK), H, B);
-    launch_kernel(lm_attention_fwd_kernel, dim3(grid), dim3(128), 0, s, qkv, valid, o, lse, T, H, kv_cache, Tmax);
+    if (kv_cache != nullptr) launch_kernel(lm_attention_fwd_kernel<true>, dim3(grid), dim3(128), 0, s, qkv, valid, o, lse, T, H, kv_cache, Tmax);
+    else launch_kernel(lm_attention_fwd_kernel<false>, dim3(grid), dim3(128), 0, s, qkv, valid, o, lse, T, H, kv_cache, Tmax);
     KERNEL_CHECK();
     count_launch();
 }
