@@ -365,3 +365,23 @@ def test_decode_attention_long_history_crosses_the_staging_limit():
         checked += n
         longest = max(longest, n)
     assert checked >= 24 and longest >= 10      # the comparison reaches past the 224-key switch (decode step 7)
+
+
+@pytest.mark.parametrize("batch,text_len,mapping", [(1, 3, "mlp"), (3, 100, "transformer"), (2, 64, "mlp"), (5, 55, "transformer")])
+def test_train_step_edge_shapes(batch, text_len, mapping):
+    """Shapes off the beaten path, against the live oracle: a single caption of three tokens (13 rows: one partial GEMM tile),
+    sequences longer than one 64-row attention block (the multi-block backward with its fp32 dQ scratch), T = 64 + prefix
+    exactly across the block boundary, odd batch sizes."""
+    from oracle.cases import _case
+    case = _case("train", "gpt2-tiny", mapping, batch, text_len, 64, 4, 4, 2, ragged=True, n_positions=256)
+    lm_w, mapper_w, b, cfg = build_case(case)
+    model = build_model(case, lm_w, mapper_w)
+    out = model(question_tokens=b["input_ids"], labels=b["labels"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"])
+    out.loss.backward()
+    loss = float(out.loss.detach())
+    loss_o, grads_o = orc.train_step(lm_w, mapper_w, cfg, b["input_ids"], b["clip_embeddings"], b["attention_mask"], b["labels"])
+    assert abs(loss - loss_o) / abs(loss_o) <= LOSS_RTOL, (loss, loss_o)
+    got = torch.cat([p.grad.flatten() for p in model.parameters()])
+    ref = torch.cat([grads_o[k].flatten() for k in grads_o])
+    assert torch.isfinite(got).all()
+    assert cosine(got, ref) >= GRAD_COS
