@@ -72,7 +72,7 @@ def _check_search(q, db, k):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("M,N,D,k", [(37, 1000, 64, 1), (37, 1000, 64, 5), (5, 300, 8, 300), (3, 40, 16, 64), (1100, 5000, 32, 16),
-                                     (16, 20000, 768, 100)])
+                                     (16, 20000, 768, 100), (1, 1001, 24, 7), (9, 16385, 16, 2048), (2, 33001, 8, 1500)])
 def test_rices_search_matches_oracle(M, N, D, k):
     g = np.random.default_rng(M * 1000 + k)
     q, db = g.standard_normal((M, D)).astype(np.float32), (g.standard_normal((N, D)) * 3).astype(np.float32)
