@@ -385,3 +385,28 @@ def test_train_step_edge_shapes(batch, text_len, mapping):
     ref = torch.cat([grads_o[k].flatten() for k in grads_o])
     assert torch.isfinite(got).all()
     assert cosine(got, ref) >= GRAD_COS
+
+
+def test_generate_eos_bookkeeping_and_single_row():
+    """EOS handling against the live oracle (clipcap.py:423-463): the raw argmax keeps being fed back after a row has
+    finished, finished rows are padded, and the loop stops as soon as every row has produced EOS.  The EOS id is chosen
+    from what the model actually generates, so rows finish at different steps.  Also a batch of one."""
+    case = CASES["gen_tiny_prepend"]
+    lm_w, mapper_w, batch, cfg = build_case(case)
+    model = build_model(case, lm_w, mapper_w).eval()
+    args = dict(question_tokens=batch["input_ids"], prefix=batch["clip_embeddings"], question_mask=batch["attention_mask"])
+    free = model.generate(max_length=8, pad_token_id=case["pad_token_id"], eos_token_id=None, **args)
+    model.gpt.config.eos_token_id = None
+    ref_free, margins = orc.generate(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"], batch["attention_mask"],
+                                     max_length=8, pad_token_id=case["pad_token_id"], eos_token_id=None, return_margins=True)
+    if float(margins.min()) < 0.05 or free != ref_free:
+        pytest.skip("near-tie in the free-running decode: EOS positions would not be comparable")
+    for eos in sorted({row[1] for row in free} | {free[0][0]}):          # ids that appear early in some rows
+        kw = dict(max_length=8, pad_token_id=case["pad_token_id"], eos_token_id=int(eos))
+        got = model.generate(**args, **kw)
+        ref = orc.generate(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"], batch["attention_mask"], **kw)
+        assert got == ref, (eos, got, ref)
+        assert any(case["pad_token_id"] in row for row in got) or len(got[0]) < 8 or all(eos not in row[:-1] for row in got)
+    one = model.generate(question_tokens=batch["input_ids"][:1], prefix=batch["clip_embeddings"][:1],
+                         question_mask=batch["attention_mask"][:1], max_length=8, pad_token_id=case["pad_token_id"], eos_token_id=None)
+    assert one == free[:1]
