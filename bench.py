@@ -4,7 +4,7 @@
     python bench.py --gpus 1 --steps 20 --warmup 3                      # this repo's CUDA path
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W                       # data-parallel, weak scaling (256 samples / GPU)
-    python bench.py --impl reference --steps K --warmup W               # the CPU port of the reference path (oracle)
+    python bench.py --impl reference --steps K --warmup W               # the reference's own CPU path on the host cores
 
 One JSON line on stdout (rank 0).  A "step" = forward + backward-to-the-mapper + caption cross-entropy of one
 synthetic Conceptual-Captions batch (BASELINE.json configs[1]: GPT-2 small, transformer mapper, batch 256 per
@@ -43,7 +43,6 @@ WORKLOAD_TEXT = {
           "(T=50), synthetic CLIP ViT-L/14 768-d embeddings, 64 samples per GPU (512 on 8 GPUs)",
 }
 WORKLOAD = "c2"
-CPU_SAMPLE_BATCH = 8                 # bounded CPU sample: the same config at batch 8
 
 
 def peaks():
@@ -91,42 +90,74 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ---- the CPU port of the reference path (oracle), used for --impl reference and cpu_baseline --------------------
-def cpu_reference(steps: int, warmup: int):
+# ---- the reference's CPU implementation of the path, used for --impl reference and cpu_baseline ----------------------
+C1 = dict(model_version="gpt2", mapping_type="mlp", prefix_length=10, clip_length=10, clip_dim=512, num_layers=8,
+          batch=8, text_len=40, vocab=50257)          # BASELINE configs[0]: the reference's own CPU-runnable case
+REF_ARM_BATCH = 64                                     # --impl reference: bounded sample of the 256-caption step
+
+
+def cpu_reference(W, batch, steps: int, warmup: int):
+    """Time forward + backward of the caption step on the host cores.  Runs the UNMODIFIED reference module
+    (``ClipCaptionPrefix`` of clipcap.py, imported from oracle/_ref -- see oracle/install_reference.py) when its file
+    travelled with the snapshot (kind "reference"), else the pinned oracle port (kind "port").  Median over `steps`."""
     from oracle import clip_prefix_lm as orc
+    from oracle import reference_shim
     import eavqa_b200.synthetic as syn
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg_lm = syn.lm_config(C2["model_version"], vocab=C2["vocab"])
+    cfg_lm = syn.lm_config(W["model_version"], vocab=W["vocab"])
     lm_w = syn.make_lm_weights(cfg_lm, seed=0)
-    mapper_w = syn.make_mapper_params(C2["mapping_type"], C2["clip_dim"], cfg_lm["d_model"], C2["prefix_length"], C2["clip_length"],
-                                      C2["num_layers"], seed=1)
-    batch = syn.make_caption_batch(CPU_SAMPLE_BATCH, C2["text_len"], C2["clip_dim"], C2["vocab"], seed=2021)
-    cfg = dict(n_layer=cfg_lm["n_layer"], n_head=cfg_lm["n_head"], d_model=cfg_lm["d_model"], prefix_length=C2["prefix_length"],
-               clip_length=C2["clip_length"], mapping_type=C2["mapping_type"], num_layers=C2["num_layers"])
-    times = []
+    mapper_w = syn.make_mapper_params(W["mapping_type"], W["clip_dim"], cfg_lm["d_model"], W["prefix_length"], W["clip_length"],
+                                      W["num_layers"], seed=1, perturb_norm=True)
+    b = syn.make_caption_batch(batch, W["text_len"], W["clip_dim"], W["vocab"], seed=2021)
+    kind = "reference" if reference_shim.reference_dir() is not None else "port"
+    if kind == "reference":
+        clipcap, _, GPT2Config, holder = reference_shim.import_reference()
+        ref = reference_shim.build_reference_model(clipcap, GPT2Config, holder, cfg_lm, lm_w, mapper_w,
+                                                   prefix_length=W["prefix_length"], clip_length=W["clip_length"],
+                                                   clip_dim=W["clip_dim"], num_layers=W["num_layers"], mapping_type=W["mapping_type"])
+
+        def one():
+            ref.zero_grad(set_to_none=True)
+            out = ref(question_tokens=b["input_ids"], labels=b["labels"], prefix=b["clip_embeddings"],
+                      question_mask=b["attention_mask"], pad_token_id=50256)
+            out.loss.backward()
+            return float(out.loss)
+        what = "the unmodified reference module (clipcap.ClipCaptionPrefix over HF GPT2LMHeadModel)"
+    else:
+        cfg = dict(n_layer=cfg_lm["n_layer"], n_head=cfg_lm["n_head"], d_model=cfg_lm["d_model"], prefix_length=W["prefix_length"],
+                   clip_length=W["clip_length"], mapping_type=W["mapping_type"], num_layers=W["num_layers"])
+
+        def one():
+            return orc.train_step(lm_w, mapper_w, cfg, b["input_ids"], b["clip_embeddings"], b["attention_mask"], b["labels"])[0]
+        what = "the pinned oracle port (oracle/clip_prefix_lm.py; the reference's file did not travel to this box)"
+    times, loss = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        orc.train_step(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"], batch["attention_mask"], batch["labels"])
+        loss = one()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    return dict(value=CPU_SAMPLE_BATCH / sec, unit="samples/s", cores=torch.get_num_threads(), kind="port",
-                sample="same config at batch %d (fp32, %d timed steps of forward+backward, oracle/clip_prefix_lm.py)" % (CPU_SAMPLE_BATCH, steps),
-                ms_per_step=sec * 1e3)
+    sec = statistics.median(times)
+    return dict(value=batch / sec, unit="samples/s", cores=torch.get_num_threads(), kind=kind, ms_per_step=sec * 1e3, loss=loss,
+                sample="%s, fp32, %s mapper, GPT-2 small, batch %d, text 40: zero_grad + forward + loss.backward(), %d warm-up + "
+                       "%d timed steps, median" % (what, W["mapping_type"], batch, warmup, steps))
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation on THIS arm's configuration (configs[1]: transformer mapper,
+    GPT-2 small), each step a bounded sample of the 256-caption batch."""
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 40)), max(1, min(args.warmup, 5))
-    r = cpu_reference(steps, warmup)
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    r = cpu_reference(C2, REF_ARM_BATCH, steps, warmup)
+    cfg = workload_config(1, note="reference CPU path on the host cores; every step is a bounded sample of the workload: "
+                                  "%d of the 256 captions of a step (a CPU step of 256 takes ~4x as long at the same rate)" % REF_ARM_BATCH)
+    cfg.update(batch_per_gpu=REF_ARM_BATCH, global_batch=REF_ARM_BATCH, parallelism="cpu", optimizer="none (forward + backward only)")
     line = {"impl": "reference", "metric": "mapper_train_samples_per_sec", "value": r["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(1, note="CPU port of the reference path on the host cores; bounded sample"),
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "loss": r["loss"], "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -191,11 +222,15 @@ def main():
 
     lm_cfg = syn.lm_config(W["model_version"], vocab=W["vocab"])
     lm_w = syn.make_lm_weights(lm_cfg, seed=0)
-    torch.manual_seed(1)
     model = eavqa_b200.ClipCaptionPrefixB200(prefix_length=W["prefix_length"], clip_length=W["clip_length"],
                                              prefix_size=W["clip_dim"], num_layers=W["num_layers"],
                                              mapping_type=W["mapping_type"], model_version=W["model_version"],
-                                             lm_state_dict=lm_w).to(dev).train()
+                                             lm_state_dict=lm_w)
+    # mapper weights: the seeded generator of the parity cases (oracle/cases.py), so that rank 0's first batch of the c2
+    # workload IS the case `train_c2_full_b256` whose reference loss is committed under tests/golden/
+    model.clip_project.load_state_dict(syn.make_mapper_params(W["mapping_type"], W["clip_dim"], lm_cfg["d_model"], W["prefix_length"],
+                                                              W["clip_length"], W["num_layers"], seed=1, perturb_norm=True))
+    model = model.to(dev).train()
     B = W["batch_per_gpu"]
     if args.scaling == "strong":
         assert B % world == 0, "strong scaling needs the global batch to divide by the number of GPUs"
@@ -241,6 +276,24 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         barrier()
         return float(ms) / n
+
+    # ---- parity guard: the loss of the step's first forward against the UNMODIFIED reference's loss on the same inputs
+    #      (tests/golden/train_c2_full_b256.json, written by oracle/validate_against_reference.py); bar 1e-3 relative
+    loss_check = None
+    fixture = os.path.join(ROOT, "tests", "golden", "train_c2_full_b256.json")
+    with torch.no_grad():
+        loss0 = float(model(question_tokens=resident["input_ids"], labels=resident["labels"], prefix=resident["clip_embeddings"],
+                            question_mask=resident["attention_mask"]).loss)
+    assert loss0 == loss0 and abs(loss0) < 1e4, "bench.py: the step's loss is not finite (%r)" % loss0
+    if WORKLOAD == "c2" and B == C2["batch_per_gpu"] and rank == 0 and os.path.exists(fixture):
+        with open(fixture) as f:
+            ref_loss = json.load(f)["loss"]
+        rel = abs(loss0 - ref_loss) / abs(ref_loss)
+        loss_check = {"loss": loss0, "reference_loss": ref_loss, "rel_err": rel, "bar": 1e-3,
+                      "fixture": "tests/golden/train_c2_full_b256.json (the reference module's fp32 loss on these 256 captions)"}
+        assert rel <= 1e-3, "bench.py: loss %.6f differs from the reference's %.6f by %.2e (> 1e-3)" % (loss0, ref_loss, rel)
+    else:
+        loss_check = {"loss": loss0, "reference_loss": None, "note": "no committed reference loss for this workload / shard"}
 
     # ---- kernel-resident throughput: inputs already in HBM ---------------------------------------------------------
     for _ in range(args.warmup):
@@ -314,7 +367,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": dict(workload_config(world), batch_per_gpu=B, global_batch=B * world),
             "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "roofline": roofline}
+            "gpu_launches": int(launches), "roofline": roofline, "loss_check": loss_check}
 
     # ---- few-shot VQA answers/s (BASELINE configs[3]) and the CPU baseline: rank 0, N = 1 only ------------------------
     if reducer is not None:
@@ -328,7 +381,8 @@ def main():
     if world == 1 and not args.no_rices:
         line["rices_retrieval"] = bench_rices(with_cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(steps=6, warmup=2)
+        # BASELINE configs[0] exactly: MLP mapper, batch 8, 3 warm-up + 10 timed steps, median
+        r = cpu_reference(C1, C1["batch"], steps=10, warmup=3)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -379,7 +433,7 @@ def bench_rices(with_cpu=True):
     (k = 2048) over a VQA2-train-sized database of CLIP text embeddings, 4096 queries per call."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import rices_bench
-    r = rices_bench.run(M=4096, N=443757, D=768, k=2048, reps=3)
+    r = rices_bench.run(M=4096, N=443757, D=768, k=2048, reps=10)
     if with_cpu:
         import numpy as np
         from oracle import rices as orc

@@ -104,6 +104,15 @@ int eavqa_train_step(eavqa_handle* h, int32_t batch, int32_t text_len, const flo
     API_END
 }
 
+int eavqa_forward_logits(eavqa_handle* h, int32_t batch, int32_t text_len, const float* clip, const int64_t* tokens,
+                         const int64_t* mask, const float* params, float* logits_out, int64_t ld, void* stream) {
+    API_BEGIN
+    EAVQA_CHECK(h != nullptr, "null handle");
+    EAVQA_CHECK(logits_out != nullptr, "null logits_out");
+    h->engine->train_step(batch, text_len, clip, tokens, mask, nullptr, params, nullptr, nullptr, S(stream), logits_out, ld);
+    API_END
+}
+
 int eavqa_generate(eavqa_handle* h, int32_t batch, int32_t text_len, int32_t n_images, const float* clip,
                    const int64_t* tokens, const int64_t* mask, int64_t sentinel_lo, int64_t sentinel_hi,
                    const float* params, int32_t max_new, int32_t has_eos, int64_t pad_id, int64_t eos_id,

@@ -584,10 +584,13 @@ static void lm_block(const LmLayer& w, int d, int H, const LmBlockIO& io, cudaSt
 
 // ============================================================================================ training step
 void Engine::train_step(int B, int Tt, const float* clip, const int64_t* tokens, const int64_t* mask, const int64_t* labels,
-                        const float* params, float* grads, float* loss_out, cudaStream_t s) {
+                        const float* params, float* grads, float* loss_out, cudaStream_t s, float* logits_all, int64_t ld_logits) {
     EAVQA_CHECK(finalized_, "LM weights not loaded (call eavqa_finalize_lm)");
     EAVQA_CHECK(B > 0 && Tt > 0, "empty batch");
-    EAVQA_CHECK(clip && tokens && labels && params && loss_out, "null argument");
+    EAVQA_CHECK(clip && tokens && params, "null argument");
+    EAVQA_CHECK(logits_all != nullptr || (labels && loss_out), "null argument");
+    EAVQA_CHECK(logits_all == nullptr || (grads == nullptr && ld_logits >= Vpad_ && ld_logits % 4 == 0 && ld_logits < (1ll << 31)),
+                "forward_logits: forward only, row stride >= vocab rounded up to 64");
     const int d = d_, L = L_, T = P_ + Tt, M = B * T, Mh = B * Tt;
     EAVQA_CHECK(T <= cfg_.n_positions, "sequence longer than n_positions");
     const bool bwd = grads != nullptr;
@@ -664,6 +667,12 @@ void Engine::train_step(int B, int Tt, const float* clip, const int64_t* tokens,
         lm_block(layers_[l], d, H_, io, s);
     }
     const float* h_last = h[hi(2 * L)];
+    if (logits_all != nullptr) {
+        // HF modeling_gpt2.py:628,706: ln_f and the tied head on EVERY position, fp32 logits (clipcap.py:337-342 `.logits`)
+        layernorm_fwd(h_last, d, nullptr, lnf_g_, lnf_b_, u, d, nullptr, nullptr, M, d, 1e-5f, s);
+        gemm(u, d, wte_bf16_, d, M, Vpad_, d, ep_f32(logits_all, static_cast<int>(ld_logits)), s);
+        return;
+    }
 
     // ---- tied LM head + shifted cross-entropy on the rows that carry a target
     //      (HF modeling_gpt2.py:703-716, loss_utils.py:28-67); [B*T, V] logits are never materialised in fp32

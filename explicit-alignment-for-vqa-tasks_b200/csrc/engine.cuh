@@ -61,8 +61,11 @@ public:
     void set_grad_events(void* const* events, int n);
     int64_t mapper_param_count() const { return mapper_count_; }
 
+    // logits_all != null (eavqa_forward_logits): forward only, the tied head runs on every position into
+    // logits_all [B * T, ld_logits] fp32 and no loss is computed (labels / loss_out may then be null)
     void train_step(int B, int Tt, const float* clip, const int64_t* tokens, const int64_t* mask, const int64_t* labels,
-                    const float* params, float* grads, float* loss_out, cudaStream_t s);
+                    const float* params, float* grads, float* loss_out, cudaStream_t s, float* logits_all = nullptr,
+                    int64_t ld_logits = 0);
     void generate(int B, int Tt, int n_images, const float* clip, const int64_t* tokens, const int64_t* mask,
                   int64_t sent_lo, int64_t sent_hi, const float* params, int max_new, int has_eos, int64_t pad_id,
                   int64_t eos_id, int64_t* tokens_out, float* top_logit, float* token_logprob, int32_t* steps_out, cudaStream_t s);

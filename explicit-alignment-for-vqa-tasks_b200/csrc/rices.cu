@@ -257,6 +257,17 @@ __global__ void __launch_bounds__(256) rices_rerank_kernel(const float* __restri
     (void)n_valid;
 }
 
+// per-query pool state at the start of a query block: empty pool, threshold -inf (on the device: no host staging buffer)
+__global__ void rices_pool_reset_kernel(int* __restrict__ pool_n, float* __restrict__ pool_thr, int n) {
+    pdl_trigger();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        pool_n[i] = 0;
+        pool_thr[i] = -INFINITY;
+    }
+}
+
 int select_cap(int k) { return k + std::max(k, 1024); }      // the pool always has room for one 1024-column batch beyond k
 
 // workspace kept between calls (grow-only): the index build of a 444k x 768 database needs 2 GB, and cudaMalloc / cudaFree
@@ -315,15 +326,16 @@ void rices_search(const float* queries, const float* database, int64_t M, int64_
     launch_kernel(rices_normalize_split_kernel, dim3(static_cast<unsigned>(ceil_div64(N, 8))), dim3(256), 0, s, database, N, D, db.p, 1);
     KERNEL_CHECK();
     count_launch();
-    std::vector<float> neg_inf(static_cast<size_t>(Mc), -INFINITY);
     for (int64_t m0 = 0; m0 < M; m0 += Mc) {
         const int64_t mc = std::min(Mc, M - m0);
         launch_kernel(rices_normalize_split_kernel, dim3(static_cast<unsigned>(ceil_div64(mc, 8))), dim3(256), 0, s, queries + m0 * D, mc, D,
                       q.p, 0);
         KERNEL_CHECK();
         count_launch();
-        CUDA_CHECK(cudaMemsetAsync(pool_n.p, 0, sizeof(int) * mc, s));
-        CUDA_CHECK(cudaMemcpyAsync(pool_thr.p, neg_inf.data(), sizeof(float) * mc, cudaMemcpyHostToDevice, s));
+        launch_kernel(rices_pool_reset_kernel, dim3(static_cast<unsigned>(ceil_div64(mc, 256))), dim3(256), 0, s, pool_n.p, pool_thr.p,
+                      static_cast<int>(mc));
+        KERNEL_CHECK();
+        count_launch();
         for (int64_t n0 = 0; n0 < N; n0 += Nc) {
             const int64_t nc = std::min(Nc, N - n0);
             GemmArgs a;

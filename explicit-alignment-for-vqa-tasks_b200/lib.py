@@ -39,6 +39,8 @@ PROTOTYPES = {
                                            C.POINTER(c_int64)]),
     "eavqa_train_step": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
+    "eavqa_forward_logits": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                       c_void_p]),
     "eavqa_generate": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                  c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_void_p, C.POINTER(c_int32),
                                  c_void_p]),

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import os
 import types
 from collections import OrderedDict
 from typing import Dict, List, Optional
@@ -80,11 +81,12 @@ class _TransformerMapperParams(nn.Module):                     # clipcap.py:223-
 
 class _StepOutput:
     """What ``ClipCaptionModel.forward`` returns to the executor: ``.loss`` (0-d, differentiable w.r.t. the
-    mapper) and ``.logits`` (not materialised: [B, T, V] fp32 would be 2.6 GB at B=256; ``None``)."""
+    mapper) and ``.logits`` -- ``None`` unless ``forward(..., return_logits=True)`` asked for them (the step never
+    materialises [B, T, V] fp32: 2.6 GB at B=256; the executors only read ``.loss``)."""
 
-    def __init__(self, loss):
+    def __init__(self, loss, logits=None):
         self.loss = loss
-        self.logits = None
+        self.logits = logits
 
     def __getitem__(self, i):
         return (self.loss, self.logits)[i]
@@ -170,6 +172,7 @@ class ClipCaptionModelB200(nn.Module):
         self._slices: List[tuple] = []
         self._param_list: List[nn.Parameter] = []
         self.last_flat_grads = None
+        self.save_lm = False           # state_dict() also emits the frozen LM (reference checkpoint layout) when True
 
     # ------------------------------------------------------------------ LM weights
     @staticmethod
@@ -182,14 +185,25 @@ class ClipCaptionModelB200(nn.Module):
             if lm_config:
                 cfg.update(lm_config)
             return cfg, OrderedDict((k, v.detach().float().cpu()) for k, v in sd.items())
-        try:        # a locally cached HF checkpoint, when one exists (never downloads)
-            from transformers import GPT2LMHeadModel
-            hf = GPT2LMHeadModel.from_pretrained(model_version, local_files_only=True)
-            return ClipCaptionModelB200._resolve_lm(model_version, hf.state_dict(), None)
-        except Exception:
-            cfg = synthetic.lm_config(model_version) if lm_config is None else dict(lm_config)
-            logger.warning("no local HF checkpoint for %r: using seeded synthetic GPT-2 weights (%s)", model_version, cfg)
+        # Synthetic (seeded random-init) weights are an explicit opt-in: the test-only shapes "gpt2-tiny" / "gpt2-mini",
+        # a "synthetic:<name>" model_version, or EAVQA_SYNTHETIC_LM=1 in the environment (offline boxes).  Anything else is
+        # a real checkpoint name and resolves exactly like the reference's GPT2LMHeadModel.from_pretrained (clipcap.py:252):
+        # local cache or download, and an error when neither works -- never a silent random LM.
+        name = model_version or ""
+        synthetic_name = name[len("synthetic:"):] if name.startswith("synthetic:") else None
+        if synthetic_name is None and (name in ("gpt2-tiny", "gpt2-mini") or os.environ.get("EAVQA_SYNTHETIC_LM") == "1"):
+            synthetic_name = name
+        if synthetic_name is not None:
+            cfg = synthetic.lm_config(synthetic_name) if lm_config is None else dict(lm_config)
+            logger.warning("using seeded SYNTHETIC GPT-2 weights for %r (%s)", model_version, cfg)
             return cfg, synthetic.make_lm_weights(cfg, seed=0)
+        from transformers import GPT2LMHeadModel
+        try:
+            hf = GPT2LMHeadModel.from_pretrained(model_version)
+        except OSError as e:        # no cached checkpoint and no way to fetch one
+            raise OSError("cannot load the GPT-2 checkpoint %r (%s).  Pass lm_state_dict=..., or opt in to seeded synthetic "
+                          "weights with model_version='synthetic:%s' / EAVQA_SYNTHETIC_LM=1" % (model_version, e, model_version)) from e
+        return ClipCaptionModelB200._resolve_lm(model_version, hf.state_dict(), None)
 
     def _resize_vocab(self, n: int):
         wte = self._lm_weights["transformer.wte.weight"]
@@ -308,20 +322,36 @@ class ClipCaptionModelB200(nn.Module):
         return loss, grads
 
     def forward(self, question_tokens: torch.Tensor, prefix: torch.Tensor, question_mask: Optional[torch.Tensor] = None,
-                labels: Optional[torch.Tensor] = None, pad_token_id=None):
-        """clipcap.py:290-342.  ``labels`` are the un-shifted text labels (-100 = ignore); the shift happens inside."""
+                labels: Optional[torch.Tensor] = None, pad_token_id=None, return_logits: bool = False):
+        """clipcap.py:290-342.  ``labels`` are the un-shifted text labels (-100 = ignore); the shift happens inside.
+        ``return_logits=True`` additionally fills ``.logits`` ([B, T, V] fp32, detached; one more forward pass through
+        ``eavqa_forward_logits`` -- meant for small batches); without ``labels`` only the logits are computed and
+        ``.loss`` is ``None``, as for the reference's HF output."""
         self._ensure_engine()
         tokens = self._prep(question_tokens, torch.int64)
         clip = self._prep(prefix, torch.float32).reshape(tokens.shape[0], -1)
         if clip.shape[1] != self.prefix_size:
             raise ValueError("prefix must hold one %d-d CLIP embedding per sample" % self.prefix_size)
         mask = self._prep(question_mask, torch.int64) if question_mask is not None else None
+        if labels is None and not return_logits:
+            raise ValueError("ClipCaptionPrefixB200.forward computes the caption loss and needs `labels` "
+                             "(or return_logits=True for the logits alone)")
+        logits = None
+        if return_logits:
+            B, Tt = tokens.shape
+            V = self._lm_cfg["vocab"]
+            ld = (V + 63) // 64 * 64
+            buf = torch.empty(B, self.prefix_length + Tt, ld, dtype=torch.float32, device=self._flat.device)
+            with torch.cuda.device(self._flat.device):
+                _lib.check(_lib.load().eavqa_forward_logits(self._handle, B, Tt, clip.data_ptr(), tokens.data_ptr(), _lib.ptr(mask),
+                                                            self._flat.data_ptr(), buf.data_ptr(), ld, _lib.current_stream()))
+            logits = buf[:, :, :V]
         if labels is None:
-            raise ValueError("ClipCaptionPrefixB200.forward computes the caption loss and needs `labels`")
+            return _StepOutput(None, logits)
         labels = self._prep(labels, torch.int64)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)
         loss = _TrainStepFn.apply(self, need_grad, clip, tokens, mask, labels, *self._param_list)
-        return _StepOutput(loss)
+        return _StepOutput(loss, logits)
 
     @torch.no_grad()
     def generate(self, question_tokens: torch.Tensor, prefix: torch.Tensor, question_mask: Optional[torch.Tensor] = None,
@@ -373,14 +403,29 @@ class ClipCaptionModelB200(nn.Module):
         return out.cpu().numpy().astype(int).tolist()                                              # clipcap.py:469
 
     # ------------------------------------------------------------------ checkpoints
-    def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        """Accepts a reference checkpoint: ``clip_project.*`` go to the mapper, ``gpt.*`` (the frozen LM the
-        reference's checkpoints also carry) are re-packed into the engine."""
-        lm = {k: v for k, v in state_dict.items() if k.startswith("gpt.")}
-        rest = OrderedDict((k, v) for k, v in state_dict.items() if not k.startswith("gpt."))
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """Reference checkpoints also carry the frozen LM (``gpt.transformer.*``, ``gpt.lm_head.weight``).
+        ``self.gpt`` is not an ``nn.Module`` here, so those keys are taken out of the incoming dict and re-packed into the
+        engine.  This is the hook ``nn.Module.load_state_dict`` calls on every sub-module, so it also works when the
+        model is nested (Lightning loads a checkpoint through the executor: keys ``model.gpt.*``) and with ``strict=True``."""
+        lm_prefix = prefix + "gpt."
+        lm = {k[len(prefix):]: state_dict.pop(k) for k in [k for k in state_dict if k.startswith(lm_prefix)]}
         if lm:
             self.load_lm_state_dict(lm)
-        return super().load_state_dict(rest, strict=strict, **kw)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+    def state_dict(self, *args, include_lm: Optional[bool] = None, **kwargs):
+        """``clip_project.*`` with the reference's names and shapes.  ``include_lm=True`` (or ``self.save_lm = True``, for
+        callers such as Lightning that cannot pass the argument) adds the frozen LM under the reference's ``gpt.*`` keys,
+        so the result strict-loads into the reference's ``ClipCaptionPrefix``."""
+        sd = super().state_dict(*args, **kwargs)
+        if include_lm if include_lm is not None else self.save_lm:
+            prefix = kwargs.get("prefix", args[1] if len(args) > 1 else "")
+            for k, v in self._lm_weights.items():
+                if k != "lm_head.weight" and not k.endswith(".attn.bias") and not k.endswith(".attn.masked_bias"):
+                    sd[prefix + "gpt." + k] = v
+            sd[prefix + "gpt.lm_head.weight"] = self._lm_weights["transformer.wte.weight"]      # tied head
+        return sd
 
 
 class ClipCaptionPrefixB200(ClipCaptionModelB200):

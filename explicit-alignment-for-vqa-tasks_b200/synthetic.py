@@ -40,12 +40,17 @@ def lm_config(model_version: str, vocab: Optional[int] = None, n_positions: Opti
     return cfg
 
 
-def make_lm_weights(cfg: dict, seed: int = 0, hot_rows: int = 0) -> "OrderedDict[str, torch.Tensor]":
+def make_lm_weights(cfg: dict, seed: int = 0, hot_rows: int = 0, successor: Optional[dict] = None) -> "OrderedDict[str, torch.Tensor]":
     """HF-default-like init (every matrix ~ N(0, 0.02^2)) with *non-trivial* biases and
     LayerNorm affines (HF's are 0 / 1 / 0, which would hide bias / gamma / beta bugs).
 
     ``hot_rows > 0`` multiplies that many seeded ``wte`` rows by 8 ("sharpened" LM, SURVEY.md
-    section 7.3) so that greedy decoding has non-degenerate top-2 margins.
+    section 7.3) so that greedy decoding has non-degenerate top-2 margins.  With tied embeddings a hot token mostly
+    predicts itself, so those decodes repeat one token.
+
+    ``successor`` (a dict, see ``plant_successor_table``) instead plants a bigram table in the first block's MLP:
+    every hot token robustly predicts ANOTHER hot token (one seeded cycle through the hot set), so greedy answers
+    are chains of distinct tokens whose top-2 margins sit a few logit standard deviations above bf16 noise.
     """
     g = torch.Generator().manual_seed(seed)
     d, L, V, NP = cfg["d_model"], cfg["n_layer"], cfg["vocab"], cfg["n_positions"]
@@ -73,11 +78,62 @@ def make_lm_weights(cfg: dict, seed: int = 0, hot_rows: int = 0) -> "OrderedDict
         w[p + "mlp.c_proj.weight"] = mat(4 * d, d)
         w[p + "mlp.c_proj.bias"] = mat(d)
     ln("transformer.ln_f", w)
-    if hot_rows:
+    if successor is not None:
+        plant_successor_table(w, cfg, **successor)
+    elif hot_rows:
         gh = torch.Generator().manual_seed(7)
         idx = torch.randperm(V, generator=gh)[:hot_rows]
         w["transformer.wte.weight"][idx] *= 8.0
     return w
+
+
+def successor_hot_ids(n_hot: int, text_vocab: int) -> torch.Tensor:
+    """The seeded hot-token set of the successor-planted LM: ``n_hot`` ids below ``text_vocab`` (so that neither the
+    pad / eos id nor an added sentinel is ever hot).  Token ``ids[i]`` is followed by ``ids[(i + 1) % n_hot]``."""
+    gh = torch.Generator().manual_seed(7)
+    return torch.randperm(text_vocab, generator=gh)[:n_hot]
+
+
+def plant_successor_table(w: "OrderedDict[str, torch.Tensor]", cfg: dict, n_hot: int, text_vocab: int, hot_scale: float,
+                          alpha: float, theta: float, kappa: float) -> None:
+    """Make greedy decoding of the synthetic LM diverse AND numerically well-conditioned (in place).
+
+    A random-init GPT-2 has near-Gaussian logits over 50 k tokens: the top-2 margin is a fraction of the logit
+    standard deviation, so fp32 and bf16 decodes of the very same code disagree on ~30 % of 10-token answers
+     -- and scaling a few ``wte`` rows only makes every hot token predict itself.  Here:
+
+    * ``n_hot`` seeded ``wte`` rows are scaled by ``hot_scale`` (the candidates);
+    * hidden units ``2j`` and ``2j+1`` of block 0's MLP detect hot token ``j`` at the current position:
+      pre-activations ``z`` and ``z - 1`` with ``z = alpha * <LN2-normalised residual, unit(w_j)> - theta``, so that
+      ``gelu_new(z) - gelu_new(z - 1)`` is a soft 0/1 switch that does not depend on how strongly the token matched;
+    * their ``c_proj`` rows write ``+-(kappa * w_succ(j) - max(kappa, 1.3) * w_j)`` into the residual stream, which the remaining blocks
+      carry to ``ln_f``: the successor's logit gets a structural lead over the best of the other hot rows, while the
+      randomly initialised rest of the network still moves every logit by about one standard deviation, so which
+      margin a step ends up with depends on the whole context (attention, positions, KV history).
+
+    ``alpha / theta / kappa`` come from ``oracle/calibrate_successor_lm.py`` (probe forwards of this very LM) and are
+    recorded as literals in ``oracle/cases.py``: building the weights involves no data-dependent branch.
+    """
+    d = cfg["d_model"]
+    assert 2 * n_hot <= 4 * d, "the table needs two hidden units per hot token"
+    ids = successor_hot_ids(n_hot, text_vocab)
+    wte = w["transformer.wte.weight"]
+    wte[ids] *= hot_scale
+    hot = wte[ids]                                           # [n, d]
+    unit = hot / hot.norm(dim=1, keepdim=True)
+    succ = hot[torch.roll(torch.arange(n_hot), -1)]          # row j -> embedding of the token after ids[j]
+    g2, b2 = w["transformer.h.0.ln_2.weight"], w["transformer.h.0.ln_2.bias"]
+    det = alpha * unit / g2                                  # LN2's gain divided out: the unit sees the normalised residual
+    shift = det @ b2                                         # ... and LN2's bias folded into the unit's bias
+    fc_w, fc_b = w["transformer.h.0.mlp.c_fc.weight"], w["transformer.h.0.mlp.c_fc.bias"]       # [d, 4d], [4d]
+    pr_w = w["transformer.h.0.mlp.c_proj.weight"]                                                  # [4d, d]
+    fc_w[:, 0:2 * n_hot:2] = det.t()
+    fc_w[:, 1:2 * n_hot:2] = det.t()
+    fc_b[0:2 * n_hot:2] = -theta - shift
+    fc_b[1:2 * n_hot:2] = -theta - shift - 1.0
+    write = kappa * succ - max(kappa, 1.3) * hot             # the token's own (tied-embedding) lead is always erased
+    pr_w[0:2 * n_hot:2] = write
+    pr_w[1:2 * n_hot:2] = -write
 
 
 def mapper_param_shapes(mapping_type: str, clip_dim: int, d_model: int, prefix_length: int, clip_length: int,
@@ -139,7 +195,7 @@ def make_mapper_params(mapping_type: str, clip_dim: int, d_model: int, prefix_le
 
 
 def make_caption_batch(batch: int, text_len: int, clip_dim: int, vocab: int, seed: int = 2021, ragged: bool = False,
-                       pad_token_id: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                       pad_token_id: Optional[int] = None, final_token_ids: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """Conceptual-Captions-shaped batch (``data_loader_conceptual_captions.py:78-104``):
     ``clip_embeddings [B, D]`` fp32 (raw CLIP features, un-normalised), ``input_ids`` /
     ``attention_mask`` / ``labels`` ``[B, T_text]`` int64 with pad -> -100 labels.
@@ -157,17 +213,27 @@ def make_caption_batch(batch: int, text_len: int, clip_dim: int, vocab: int, see
         ar = torch.arange(text_len).unsqueeze(0)
         mask = (ar < lens.unsqueeze(1)).long()
         tokens = torch.where(mask.bool(), tokens, torch.full_like(tokens, pad))
+    if final_token_ids is not None:        # successor-planted LM: the last VALID token of every row is a hot token
+        pick = torch.randint(0, len(final_token_ids), (batch,), generator=g)
+        last = mask.sum(dim=1) - 1
+        tokens[torch.arange(batch), last] = final_token_ids[pick]
     labels = torch.where(mask.bool(), tokens, torch.full_like(tokens, -100))
     return {"clip_embeddings": clip, "input_ids": tokens, "attention_mask": mask, "labels": labels}
 
 
 def make_fewshot_batch(batch: int, num_shots: int, clip_dim: int, vocab: int, special_token_id: int, seed: int = 2021,
-                       seg_lo: int = 10, seg_hi: int = 20, pad_token_id: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                       seg_lo: int = 10, seg_hi: int = 20, pad_token_id: Optional[int] = None,
+                       final_token_ids: Optional[torch.Tensor] = None, pad_fraction: float = 1.0) -> Dict[str, torch.Tensor]:
     """Few-shot VQA2-shaped batch (``vqa2_datasets.py:65-181``, ``module_parser.py:68-93,466-478``):
     ``clip_embeddings [B, k+1, 1, D]``; each of the k+1 segments is one sentinel id
     (``special_token_id - i``, ``vct0.py:508-509``) followed by U{seg_lo..seg_hi} text ids; rows are
     right-padded to the batch maximum (``module_parser.py:424``).  Text ids are drawn below
-    ``special_token_id - num_shots`` so that they never collide with a sentinel."""
+    ``special_token_id - num_shots`` so that they never collide with a sentinel.
+
+    ``final_token_ids`` (successor-planted LM): the last text id of every row is drawn from this set -- the analogue of
+    every VQA prompt ending in the same few "answer:" tokens -- and only ``pad_fraction`` of the rows keep their ragged
+    length; the others get their last segment stretched to the batch maximum, so that the first generated token is
+    read at a real token, not at a right-pad position (quirk Q2 stays covered by the ragged rows)."""
     g = torch.Generator().manual_seed(seed)
     pad = pad_token_id if pad_token_id is not None else min(50256, vocab - 1)
     n_img = num_shots + 1
@@ -182,6 +248,13 @@ def make_fewshot_batch(batch: int, num_shots: int, clip_dim: int, vocab: int, sp
             row.extend(torch.randint(0, text_hi, (n,), generator=g).tolist())
         rows.append(row)
     T = max(len(r) for r in rows)
+    if final_token_ids is not None:
+        keep = torch.rand(batch, generator=g) < pad_fraction
+        pick = torch.randint(0, len(final_token_ids), (batch,), generator=g)
+        for b, r in enumerate(rows):
+            if not bool(keep[b]):
+                r.extend(torch.randint(0, text_hi, (T - len(r),), generator=g).tolist())
+            r[-1] = int(final_token_ids[pick[b]])
     tokens = torch.full((batch, T), pad, dtype=torch.int64)
     mask = torch.zeros(batch, T, dtype=torch.int64)
     for b, r in enumerate(rows):

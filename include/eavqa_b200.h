@@ -80,6 +80,13 @@ int eavqa_train_step(eavqa_handle* h, int32_t batch, int32_t text_len, const flo
                      const int64_t* mask, const int64_t* labels, const float* params, float* grads, float* loss_out,
                      void* stream);
 
+/* The `.logits` of the object ClipCaptionModel.forward returns (clipcap.py:337-342: HF CausalLMOutput, logits [B, T, V]
+ * with T = prefix_length + text_len), for callers that read them.  Forward only: mapper -> concat -> L blocks -> ln_f ->
+ * tied head on EVERY position.  logits_out: device fp32 [B * T, ld] with ld >= vocab rounded up to a multiple of 64
+ * (columns >= vocab are padding).  The training step itself never materialises this tensor (2.6 GB at B = 256). */
+int eavqa_forward_logits(eavqa_handle* h, int32_t batch, int32_t text_len, const float* clip, const int64_t* tokens,
+                         const int64_t* mask, const float* params, float* logits_out, int64_t ld, void* stream);
+
 /* ClipCaptionModel.generate + _generate_from_embeddings (clipcap.py:344-471), with the k-shot prompt assembly of
  * VCT0Model.generate / insert_prefix_into_input (vct0.py:446-464,494-533) when n_images > 0.
  *   n_images = 0 : one prefix is prepended (clip [B, clip_dim]);

@@ -201,7 +201,7 @@ def train_step(lm: Dict[str, Tensor], mapper: Dict[str, Tensor], cfg: dict, ques
 def generate_from_embeddings(lm: Dict[str, Tensor], cfg: dict, embedding_cat: Tensor, attention_mask: Tensor,
                              max_length: int = 10, pad_token_id: Optional[int] = None,
                              eos_token_id: Optional[int] = None, return_margins: bool = False,
-                             return_logprobs: bool = False):
+                             return_logprobs: bool = False, top_logits_out: Optional[list] = None):
     """``ClipCaptionModel._generate_from_embeddings`` (``clipcap.py:387-471``).
 
     No KV cache: the whole sequence is re-run each step (``:416-419``); the next
@@ -229,6 +229,8 @@ def generate_from_embeddings(lm: Dict[str, Tensor], cfg: dict, embedding_cat: Te
         if return_margins:
             top2 = last.topk(2, dim=-1).values
             margins.append((top2[:, 0] - top2[:, 1]).clone())
+        if top_logits_out is not None:       # the winning logit of every step, for value-level parity of the decode
+            top_logits_out.append(last.max(dim=-1).values.clone())
         if return_logprobs:
             logprobs.append(torch.log_softmax(last.double(), dim=-1).gather(1, nxt).squeeze(1).float())
         nxt_embed = lm["transformer.wte.weight"][nxt]

@@ -98,22 +98,30 @@ def run_train_case(name, case, clipcap, GPT2Config, holder):
     print(f"[train {name}] ref loss {float(out.loss):.6f} oracle {loss_o:.6f} rel {rel:.2e}; "
           f"grad cos(min over params) {worst:.8f} rel-l2 {relg:.2e}; ref step {t_ref:.2f}s")
     assert rel < 2e-5 and worst > 0.99999 and relg < 1e-3, "oracle does not match the reference"
-    return {"kind": "train", "case": case, "loss": float(out.loss),
-            "n_valid": int((torch.nn.functional.pad(batch["labels"], (1, 0), value=-100)[:, 1:] != -100).sum()),
-            "grads": {k: grad_summary(v) for k, v in ref_grads.items()},
-            "grad_total_norm": float(flat_r.double().norm())}
+    res = {"kind": "train", "case": case, "loss": float(out.loss),
+           "n_valid": int((torch.nn.functional.pad(batch["labels"], (1, 0), value=-100)[:, 1:] != -100).sum()),
+           "grads": {k: grad_summary(v) for k, v in ref_grads.items()},
+           "grad_total_norm": float(flat_r.double().norm())}
+    if case["batch"] >= 64:
+        # full-size case: the gradient itself (167 MB) cannot be committed, so keep a seeded sample of it -- the cosine
+        # over 16384 random coordinates estimates the full one to ~1e-3
+        idx = torch.randperm(flat_r.numel(), generator=torch.Generator().manual_seed(13))[:16384]
+        res["grad_sample"] = {"seed": 13, "n": 16384, "values": [float("%.6g" % v) for v in flat_r[idx].tolist()]}
+    return res
 
 
 def run_generate_case(name, case, clipcap, vct0, GPT2Config, holder):
     lm_w, mapper_w, batch, cfg = build_case(case)
     ref = build_reference_model(clipcap, GPT2Config, holder, case, lm_w, mapper_w).eval()
     kw = dict(max_length=case["max_length"], pad_token_id=case["pad_token_id"], eos_token_id=case["eos_token_id"])
+    tops = []
+    t0 = time.time()
     with torch.no_grad():
         if case["num_shots"] is None:
             ref_tokens = ref.generate(question_tokens=batch["input_ids"], prefix=batch["clip_embeddings"],
                                       question_mask=batch["attention_mask"], **kw)
             got, margins = orc.generate(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"],
-                                        batch["attention_mask"], return_margins=True, **kw)
+                                        batch["attention_mask"], return_margins=True, top_logits_out=tops, **kw)
         else:
             # GPT-2 few-shot = the T0 path's prompt assembly (vct0.py:446-464) + clipcap's greedy loop
             B, n_img = batch["clip_embeddings"].shape[:2]
@@ -126,13 +134,30 @@ def run_generate_case(name, case, clipcap, vct0, GPT2Config, holder):
             ref_tokens = ref._generate_from_embeddings(emb, msk, **kw)
             got, margins = orc.generate_few_shot(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"],
                                                  batch["attention_mask"], case["special_token_id"],
-                                                 return_margins=True, **kw)
+                                                 return_margins=True, top_logits_out=tops, **kw)
     same = sum(int(a == b) for a, b in zip(ref_tokens, got))
-    print(f"[generate {name}] identical answers {same}/{len(ref_tokens)}; median top-2 margin "
-          f"{float(margins.median()):.4f} min {float(margins.min()):.5f}; first {ref_tokens[0]}")
-    assert same == len(ref_tokens), "oracle greedy tokens differ from the reference"
+    tops = torch.stack(tops, dim=1)
+    # how degenerate are the answers?  (round-1 review: hot-row sharpening made most rows repeat ONE token)
+    flat = [t for row in ref_tokens for t in row if t != case["pad_token_id"]]
+    one_token_rows = sum(int(len(set(row)) == 1) for row in ref_tokens if len(row) > 1)
+    mixed = sum(int(a != b) for a, b in zip(ref_tokens, got))
+    print(f"[generate {name}] identical answers {same}/{len(ref_tokens)}; top-2 margin median {float(margins.median()):.4f} "
+          f"min {float(margins.min()):.5f} (logit std over the vocabulary: see fixture); distinct tokens {len(set(flat))} in "
+          f"{len(flat)} outputs, rows repeating one token {one_token_rows}/{len(ref_tokens)}; {time.time() - t0:.0f}s; "
+          f"first {ref_tokens[0]}")
+    # fp32 summation order differs between HF's fused kernels and the restatement: a row may legitimately part ways at a
+    # step whose top-2 margin is at fp32 rounding level (seen only on the un-sharpened 128-row case)
+    for a, b, mg in zip(ref_tokens, got, margins):
+        if a != b:
+            first = next(i for i, (x, y) in enumerate(zip(a, b)) if x != y)
+            assert float(mg[first]) < 2e-4, "oracle greedy tokens differ from the reference beyond an fp32-level tie"
+    assert mixed <= max(1, len(ref_tokens) // 64), "oracle greedy tokens differ from the reference"
     return {"kind": "generate", "case": case, "tokens": ref_tokens,
-            "margins": [[round(float(x), 6) for x in row] for row in margins]}
+            "margins": [[round(float(x), 6) for x in row] for row in margins],
+            "top_logits": [[round(float(x), 5) for x in row] for row in tops],
+            "stats": {"distinct_tokens": len(set(flat)), "outputs": len(flat), "rows_repeating_one_token": one_token_rows,
+                      "margin_median": float(margins.median()), "margin_min": float(margins.min()),
+                      "top_logit_median": float(tops.median())}}
 
 
 def run_splice(vct0):

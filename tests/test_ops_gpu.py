@@ -149,9 +149,22 @@ def test_gemm_strided_operands_and_output(L):
     assert (out - ref).abs().max().item() <= 2e-3 * math.sqrt(K)
 
 
-@pytest.mark.parametrize("shape", [(256, 256, 128), (300, 200, 72), (1000, 3072, 768)], ids=lambda s: "x".join(map(str, s)))
-def test_gemm_epilogues(L, shape):
+def _gemm_variant(variant):
+    def run(L, A, B, **kw):
+        return gemm(L, A, B, block_n=variant, **kw)
+    return run
+
+
+# kernel variant = block_n + 1000 * cluster: 0 = the launcher's own heuristic (single CTAs below M = 2048, the
+# cta_group::2 pair above for the step's large shapes); 8xxx = the CTA-pair kernel forced with that tile width.
+# M >= 2048 shapes are the ones bench.py's step actually runs on the pair kernel (12800 x {768, 2304, 3072} x {768, 3072}).
+@pytest.mark.parametrize("variant", [0, 8128, 8192, 8256])
+@pytest.mark.parametrize("shape", [(256, 256, 128), (300, 200, 72), (1000, 3072, 768), (2176, 776, 264), (4224, 3072, 768),
+                                   (2560, 768, 3072)], ids=lambda s: "x".join(map(str, s)))
+def test_gemm_epilogues(L, shape, variant):
+    """Every compile-time epilogue (EpiMode) of the single-CTA AND the CTA-pair kernel against fp32 torch."""
     M, N, K = shape
+    gemm = _gemm_variant(variant)       # route every call below through the requested kernel variant
     A = _rand((M, K), 1, 0.5, torch.bfloat16)
     B = _rand((N, K), 2, 0.1, torch.bfloat16)
     bias = _rand((N,), 3)
@@ -207,10 +220,12 @@ def test_gemm_rejects_bad_arguments(L):
         gemm(L, A, B, out_fp32=True)
 
 
-def test_lmhead_ce(L):
+@pytest.mark.parametrize("M", [300, 10240], ids=["single_cta_m300", "pair_kernel_bench_head_m10240"])
+def test_lmhead_ce(L, M):
     """LM-head GEMM with fused online-softmax statistics vs torch.logsumexp on fp32 logits.
-    lse within 2e-3 absolute (bf16 operands, fp32 accumulate), target logit likewise."""
-    M, V, K = 300, 50257, 768
+    lse within 2e-3 absolute (bf16 operands, fp32 accumulate), target logit likewise.  M = 10240 is the head of bench.py's
+    step (256 captions x 40 targets, 10240 x 50304 x 768): the cta_group::2 pair kernel with the EM_CE epilogue."""
+    V, K = 50257, 768
     n_cols = (V + 63) // 64 * 64
     H = _rand((M, K), 1, 1.0, torch.bfloat16)
     W = torch.zeros(n_cols, K, device="cuda", dtype=torch.bfloat16)

@@ -11,12 +11,14 @@ import pytest
 import torch
 
 from oracle import clip_prefix_lm as orc
-from oracle.cases import CASES, SPLICE_GOLDEN, build_case
+from oracle.cases import CASES, SLOW_CASES, SPLICE_GOLDEN, build_case
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 # the two GPT-2-small/medium generate cases cost ~20-40 s each on 8 cores
-TRAIN = [k for k, v in CASES.items() if v["kind"] == "train"]
-GEN = [k for k, v in CASES.items() if v["kind"] == "generate"]
+# full-size cases (minutes of CPU each) are re-run only by oracle/validate_against_reference.py and, on the GPU box, by
+# tests/test_step_gpu.py; here their fixtures are only checked for presence and case-table agreement
+TRAIN = [k for k, v in CASES.items() if v["kind"] == "train" and k not in SLOW_CASES]
+GEN = [k for k, v in CASES.items() if v["kind"] == "generate" and k not in SLOW_CASES]
 
 
 def load(name):

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from oracle import clip_prefix_lm as orc
-from oracle.cases import CASES, build_case
+from oracle.cases import CASES, SLOW_CASES, build_case
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -45,6 +45,25 @@ TRAIN = [k for k, v in CASES.items() if v["kind"] == "train"]
 GEN = [k for k, v in CASES.items() if v["kind"] == "generate"]
 
 
+def oracle_train_step_fp32_on_gpu(lm_w, mapper_w, cfg, batch):
+    """The oracle restatement itself, executed in fp32 ON THE GPU (TF32 off): the same functions on device tensors, for
+    cases the CPU needs minutes for."""
+    with torch.device("cuda"):
+        lm_d = {k: v.cuda() for k, v in lm_w.items()}
+        mp_d = {k: v.cuda() for k, v in mapper_w.items()}
+        bd = {k: v.cuda() for k, v in batch.items()}
+        prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            loss_o, grads_o = orc.train_step(lm_d, mp_d, cfg, bd["input_ids"], bd["clip_embeddings"], bd["attention_mask"], bd["labels"])
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    grads_o = {k: v.cpu() for k, v in grads_o.items()}
+    torch.cuda.empty_cache()
+    return loss_o, grads_o
+
+
 @pytest.mark.parametrize("name", TRAIN)
 def test_train_step_parity(name):
     case = CASES[name]
@@ -58,10 +77,23 @@ def test_train_step_parity(name):
     loss = float(out.loss)
     # (1) against the reference's own number (golden fixture) and (2) against the live oracle
     assert abs(loss - fx["loss"]) / abs(fx["loss"]) <= LOSS_RTOL, (loss, fx["loss"])
-    loss_o, grads_o = orc.train_step(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"],
-                                     batch["attention_mask"], batch["labels"])
-    assert abs(loss - loss_o) / abs(loss_o) <= LOSS_RTOL
     got = {n: p.grad.detach().float().cpu() for n, p in model.clip_project.named_parameters()}
+    if name in SLOW_CASES:
+        # BASELINE configs[1] at full size (256 captions): these are the kernel variants bench.py runs -- the cta_group::2
+        # pair GEMMs with every epilogue, the 10240 x 50304 x 768 head.  The CPU oracle would need minutes and ~30 GB.
+        del model
+        torch.cuda.empty_cache()
+        loss_o, grads_o = oracle_train_step_fp32_on_gpu(lm_w, mapper_w, cfg, batch)
+        sample = fx["grad_sample"]
+        idx = torch.randperm(sum(g.numel() for g in got.values()), generator=torch.Generator().manual_seed(sample["seed"]))[:sample["n"]]
+        mine = torch.cat([g.flatten() for g in got.values()])[idx]
+        cos_ref = cosine(mine, torch.tensor(sample["values"]))
+        print(f"\n[{name}] cosine with the REFERENCE's gradient on {sample['n']} seeded coordinates: {cos_ref:.6f}")
+        assert cos_ref >= 0.998, cos_ref
+    else:
+        loss_o, grads_o = orc.train_step(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"],
+                                         batch["attention_mask"], batch["labels"])
+    assert abs(loss - loss_o) / abs(loss_o) <= LOSS_RTOL
     assert list(got.keys()) == list(grads_o.keys())
     flat_g = torch.cat([got[k].flatten() for k in got])
     flat_o = torch.cat([grads_o[k].flatten() for k in got])
@@ -92,6 +124,26 @@ def test_forward_only_matches_training_loss_and_skips_grads():
     out.loss.backward()
     assert abs(l0 - float(out.loss)) < 1e-5 * abs(l0)
     assert all(p.grad is not None for p in model.parameters())
+
+
+def test_forward_can_return_the_logits_of_every_position():
+    """``forward(..., return_logits=True).logits`` is the reference's ``[B, T, V]`` fp32 HF output (clipcap.py:337-342),
+    prefix positions included; bf16 operands, fp32 accumulate: within 5 % of the logit standard deviation."""
+    case = CASES["train_tiny_transformer"]
+    lm_w, mapper_w, batch, cfg = build_case(case)
+    model = build_model(case, lm_w, mapper_w)
+    out = model(question_tokens=batch["input_ids"], labels=batch["labels"], prefix=batch["clip_embeddings"],
+                question_mask=batch["attention_mask"], return_logits=True)
+    loss_o, logits_o = orc.caption_forward(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"],
+                                           batch["attention_mask"], batch["labels"])
+    assert out.logits.shape == logits_o.shape == (case["batch"], case["prefix_length"] + case["text_len"], case["lm"]["vocab"])
+    valid = torch.cat((torch.ones(case["batch"], case["prefix_length"]), batch["attention_mask"].float()), dim=1).bool()
+    err = (out.logits.cpu() - logits_o)[valid].abs().max().item()          # pad positions: the reference's values are arbitrary too
+    assert err <= 0.05 * logits_o[valid].std().item() + 1e-3, err
+    assert abs(float(out.loss) - float(loss_o)) <= LOSS_RTOL * abs(float(loss_o))
+    only = model(question_tokens=batch["input_ids"], prefix=batch["clip_embeddings"], question_mask=batch["attention_mask"],
+                 return_logits=True)
+    assert only.loss is None and torch.equal(only.logits, out.logits)
 
 
 def test_step_is_deterministic_and_scales_with_upstream_gradient():
@@ -153,21 +205,39 @@ def test_generate_parity(name):
     got, top = model.generate(question_tokens=batch["input_ids"], prefix=batch["clip_embeddings"],
                               question_mask=batch["attention_mask"], return_top_logits=True, **kw)
     ref, margins = fx["tokens"], fx["margins"]
+    ref_top = fx.get("top_logits")
     assert len(got) == len(ref)
-    same = 0
+    same = clear_rows = clear_same = 0
+    worst_top = 0.0
     for row, (g, r, mg) in enumerate(zip(got, ref, margins)):
-        # compare up to the first step whose fp32 top-2 margin is within bf16 reach (0.05); beyond it the
-        # two decodes legitimately follow different prefixes
+        # compare up to the first step whose fp32 top-2 margin is within bf16 reach -- 0.05 for O(1) logits, 1 % of the
+        # winning logit for the sharpened LMs (operands are rounded to 2^-9 relative); beyond it the two decodes
+        # legitimately follow different prefixes
         n = len(r)
         for i, m in enumerate(mg):
-            if m < 0.05:
+            reach = 0.05 if ref_top is None else max(0.05, 0.01 * abs(ref_top[row][i]))
+            if m < reach:
                 n = i
                 break
         assert g[:n] == r[:n], (name, row, g, r, mg)
+        if ref_top is not None:
+            # value-level parity of the decode: the winning logit of every compared step (sensitive to anything that
+            # perturbs the context -- KV order, position ids, masks -- even when the argmax survives it)
+            for i in range(min(n, top.shape[1])):
+                err = abs(float(top[row, i]) - ref_top[row][i]) / (abs(ref_top[row][i]) + 1.0)
+                worst_top = max(worst_top, err)
+                assert err <= 0.02, (name, row, i, float(top[row, i]), ref_top[row][i])
         same += int(g == r)
-    print(f"\n[{name}] identical answers {same}/{len(ref)}")
-    if case["hot_rows"]:
-        assert same >= 0.99 * len(ref)
+        clear_rows += int(n == len(r))
+        clear_same += int(n == len(r) and g == r)
+    st = fx.get("stats", {})
+    print(f"\n[{name}] identical answers {same}/{len(ref)} = {100.0 * same / len(ref):.1f} % (rows without a near-tie: "
+          f"{clear_same}/{clear_rows}); worst relative top-logit error {worst_top:.4f}; reference answers: "
+          f"{st.get('distinct_tokens', '?')} distinct tokens in {st.get('outputs', '?')} outputs, "
+          f"{st.get('rows_repeating_one_token', '?')} rows repeating one token, median top-2 margin {st.get('margin_median', float('nan')):.2f}")
+    assert clear_same == clear_rows
+    if case["hot_rows"] or case.get("successor"):
+        assert same >= 0.99 * len(ref)            # north star: identical greedy answers on >= 99 % of the prompts
         assert len(got[0]) == len(ref[0])
 
 
