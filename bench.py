@@ -97,9 +97,25 @@ REF_ARM_BATCH = 64                                     # --impl reference: bound
 
 
 def cpu_reference(W, batch, steps: int, warmup: int):
-    """Time forward + backward of the caption step on the host cores.  Runs the UNMODIFIED reference module
-    (``ClipCaptionPrefix`` of clipcap.py, imported from oracle/_ref -- see oracle/install_reference.py) when its file
-    travelled with the snapshot (kind "reference"), else the pinned oracle port (kind "port").  Median over `steps`."""
+    """Time forward + backward of the caption step on the host cores, in a child process that sees NO GPU
+    (CUDA_VISIBLE_DEVICES=""): the reference module picks its device from torch.cuda.is_available() at import
+    (clipcap.py:23), and it prints its architecture to stdout, which must not reach this process' one JSON line."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    spec = json.dumps({"W": W, "batch": batch, "steps": steps, "warmup": warmup})
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-reference-worker", spec], env=env, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("CPU reference worker failed:\n" + r.stderr[-2000:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def cpu_reference_worker(spec: str):
+    """Runs the UNMODIFIED reference module (``ClipCaptionPrefix`` of clipcap.py, imported from oracle/_ref -- see
+    oracle/install_reference.py) when its file travelled with the snapshot (kind "reference"), else the pinned oracle
+    port (kind "port").  Median over `steps`."""
+    a = json.loads(spec)
+    W, batch, steps, warmup = a["W"], a["batch"], a["steps"], a["warmup"]
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)                      # everything the reference prints goes to stderr
     from oracle import clip_prefix_lm as orc
     from oracle import reference_shim
     import eavqa_b200.synthetic as syn
@@ -137,9 +153,12 @@ def cpu_reference(W, batch, steps: int, warmup: int):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = statistics.median(times)
-    return dict(value=batch / sec, unit="samples/s", cores=torch.get_num_threads(), kind=kind, ms_per_step=sec * 1e3, loss=loss,
-                sample="%s, fp32, %s mapper, GPT-2 small, batch %d, text 40: zero_grad + forward + loss.backward(), %d warm-up + "
-                       "%d timed steps, median" % (what, W["mapping_type"], batch, warmup, steps))
+    res = dict(value=batch / sec, unit="samples/s", cores=torch.get_num_threads(), kind=kind, ms_per_step=sec * 1e3, loss=loss,
+               sample="%s, fp32, %s mapper, GPT-2 small, batch %d, text 40: zero_grad + forward + loss.backward(), %d warm-up + "
+                      "%d timed steps, median" % (what, W["mapping_type"], batch, warmup, steps))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(res), flush=True)
 
 
 def run_reference(args, rank):
@@ -169,6 +188,9 @@ def workload_config(world, note=""):
 
 
 def main():
+    if len(sys.argv) == 3 and sys.argv[1] == "--cpu-reference-worker":
+        cpu_reference_worker(sys.argv[2])
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -743,6 +743,14 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     int* part_idx = nullptr;
     unsigned* arrivals = nullptr;
     const size_t kv_layer = static_cast<size_t>(B) * Tmax * 2 * d;
+    // single-token steps: one persistent cooperative kernel per step (decode_chain.cu) instead of ~7 launches per layer
+    // (EAVQA_DECODE_CHAIN=0, read per call, selects the launch-per-operation path below: A/B measurements and tests)
+    const char* chain_opt = getenv("EAVQA_DECODE_CHAIN");
+    const bool chain_env = !(chain_opt != nullptr && chain_opt[0] == '0');
+    const bool use_chain = chain_env && max_new > 1 && B <= 128 && d % 64 == 0 && decode_chain_supported(Tmax);
+    const int n_chain = 2 + 7 * L;
+    ChainPhase* chain_dev = nullptr;
+    unsigned* chain_bar = nullptr;
     auto plan_all = [&](Arena& a) {
         const size_t m = static_cast<size_t>(M);
         mw.plan(a, *this, false);
@@ -761,6 +769,8 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         acc_qkv = a.get<float>(static_cast<size_t>(B) * 3 * d); acc_o = a.get<float>(static_cast<size_t>(B) * d);
         acc_pr = a.get<float>(static_cast<size_t>(B) * d);
         kv = a.get<bf16>(kv_layer * L);
+        chain_dev = a.get<ChainPhase>(n_chain);
+        chain_bar = a.get<unsigned>(1);
     };
     {
         arena_.begin_measure();
@@ -827,7 +837,40 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     //      step, clipcap.py:416-419; same function, 11x less work).  M = B rows per GEMM: every projection is split along K
     //      over all SMs into fp32 accumulators; bias / residual / LayerNorm / gelu live in the small kernels between them,
     //      each of which also zeroes the accumulator of the GEMM that follows.  x_a is the fp32 residual row.
-    for (int step = 1; step < max_new; ++step) {
+    if (use_chain) {
+        // the same sequence of operations as the loop below, as phases of the persistent kernel (identical for every step
+        // except `pos`, which travels as a kernel argument)
+        std::vector<ChainPhase> ph(n_chain);
+        int k = 0;
+        auto split_for = [&](int N, int K) { return std::max(1, std::min(num_sms() / (N / 64), ceil_div(K, 64))); };
+        chain_glue_phase(ph[k++], x_a, nullptr, nullptr, layers_[0].ln1_g, layers_[0].ln1_b, u, B, d, acc_qkv, 3 * d);
+        for (int l = 0; l < L; ++l) {
+            const LmLayer& w = layers_[l];
+            chain_gemm_phase(ph[k++], u, d, w.w_qkv_t, d, B, 3 * d, d, split_for(3 * d, d), CHAIN_REDUCE_F32, acc_qkv, 3 * d, nullptr);
+            chain_attn_phase(ph[k++], acc_qkv, w.b_qkv, kv + kv_layer * l, validD, Tmax, att, acc_o, B, H_, Tmax);
+            chain_gemm_phase(ph[k++], att, d, w.w_o_t, d, B, d, d, split_for(d, d), CHAIN_REDUCE_F32, acc_o, d, nullptr);
+            chain_glue_phase(ph[k++], x_a, acc_o, w.b_o, w.ln2_g, w.ln2_b, u, B, d, acc_pr, d);
+            chain_gemm_phase(ph[k++], u, d, w.w_fc_t, d, B, 4 * d, d, 1, CHAIN_GELU_BF16, fc_act, 4 * d, w.b_fc);
+            chain_gemm_phase(ph[k++], fc_act, 4 * d, w.w_pr_t, 4 * d, B, d, 4 * d, split_for(d, 4 * d), CHAIN_REDUCE_F32, acc_pr, d, nullptr);
+            if (l + 1 < L)
+                chain_glue_phase(ph[k++], x_a, acc_pr, w.b_pr, layers_[l + 1].ln1_g, layers_[l + 1].ln1_b, u, B, d, acc_qkv, 3 * d);
+            else
+                chain_glue_phase(ph[k++], x_a, acc_pr, w.b_pr, lnf_g_, lnf_b_, hc, B, d, nullptr, 0);
+        }
+        chain_gemm_phase(ph[k++], hc, d, wte_bf16_, d, B, Vpad_, d, 1, CHAIN_STORE_F32, logits, Vpad_, nullptr);
+        EAVQA_CHECK(k == n_chain, "decode chain phase count");
+        CUDA_CHECK(cudaMemcpyAsync(chain_dev, ph.data(), sizeof(ChainPhase) * n_chain, cudaMemcpyHostToDevice, s));
+        fill_zero(chain_bar, sizeof(unsigned), s);
+        unsigned epoch = 0;
+        for (int step = 1; step < max_new; ++step) {
+            launch_decode_chain(chain_dev, n_chain, T0 + step - 1, chain_bar, epoch, s);
+            epoch += static_cast<unsigned>(n_chain);
+            greedy_step(logits, Vpad_, B, V_, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out, n_unfinished, top_logit,
+                        token_logprob, wte_f32_, wpe_f32_ + static_cast<size_t>(std::min(T0 + step, cfg_.n_positions - 1)) * d, d, x_a,
+                        validD + T0 + step, Tmax, part_val, part_idx, arrivals, s);
+        }
+    }
+    for (int step = 1; step < max_new && !use_chain; ++step) {
         const int pos = T0 + step - 1;
         decode_residual_ln(x_a, nullptr, nullptr, layers_[0].ln1_g, layers_[0].ln1_b, u, B, d, 1e-5f, acc_qkv, 3 * d, s);
         for (int l = 0; l < L; ++l) {

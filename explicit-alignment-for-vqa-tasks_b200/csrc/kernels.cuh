@@ -132,6 +132,41 @@ void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf
 void lm_attention_decode_acc(const float* qkv_acc, const float* qkv_bias, bf16* cache, const int* valid, int valid_stride, bf16* o,
                              float* zero, int B, int H, int pos, int Tmax, cudaStream_t s);
 
+// ---------------------------------------------------------------- persistent decode step (decode_chain.cu)
+// One cooperative kernel per single-token step walks an array of phases (in device memory) with a grid barrier between them.
+enum ChainPhaseType { CHAIN_GEMM = 0, CHAIN_ATTN = 1, CHAIN_GLUE = 2 };
+enum ChainGemmMode {
+    CHAIN_REDUCE_F32 = 0,     // split-K: fp32 partial tiles are ADDED into `out` (TMA reduce; `out` zeroed by an earlier phase)
+    CHAIN_STORE_F32 = 1,      // fp32 out (LM head logits)
+    CHAIN_GELU_BF16 = 2,      // bf16 out = gelu_new(acc + bias) (c_fc)
+};
+struct alignas(128) ChainPhase {
+    CUtensorMap map_a, map_b, map_out;      // GEMM: A [M, K] (box 128 x 64), W [N, K] (box 64 x 64), out [M, N] (box 32 x 32)
+    int type, mode;
+    int M, N, K, split;                     // GEMM: out[M, N] (+)= A[M, K] W[N, K]^T, M <= 128 rows
+    int B, H, Tmax, valid_stride;           // ATTN: batch rows, heads, KV-cache capacity; GLUE: B = rows
+    int d, zero_n;                          // GLUE: row width; floats to zero per row of `zero`
+    const float* bias;                      // GEMM gelu bias [N] / ATTN qkv bias [3d] / GLUE projection bias [d]
+    const float* qkv_acc;                   // ATTN: fp32 q | k | v accumulator rows [B, 3d]
+    bf16* cache;                            // ATTN: this layer's KV cache
+    const int* valid;                       // ATTN: key validity [B, valid_stride]
+    bf16* o;                                // ATTN: attention output [B, d]
+    float* zero;                            // ATTN: [B, d] accumulator zeroed per (b, h); GLUE: [rows, zero_n]
+    float* x;                               // GLUE: fp32 residual rows [rows, d]
+    const float* acc;                       // GLUE: fp32 projection accumulator [rows, d] or null
+    const float *gamma, *beta;              // GLUE: LayerNorm affine
+    bf16* u;                                // GLUE: LayerNorm output [rows, d]
+};
+bool decode_chain_supported(int max_keys);  // the attention phases stage one head's whole history in shared memory
+void chain_gemm_phase(ChainPhase& p, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, int split, int mode, void* out,
+                      int ldo, const float* bias);
+void chain_attn_phase(ChainPhase& p, const float* qkv_acc, const float* qkv_bias, bf16* cache, const int* valid, int valid_stride, bf16* o,
+                      float* zero, int B, int H, int Tmax);
+void chain_glue_phase(ChainPhase& p, float* x, const float* acc, const float* bias, const float* gamma, const float* beta, bf16* u, int rows,
+                      int d, float* zero, int zero_n);
+// bar_counter: device counter zeroed once per generate call; epoch0 = grid barriers executed by earlier launches since then
+void launch_decode_chain(const ChainPhase* dev_phases, int n_phases, int pos, unsigned* bar_counter, unsigned epoch0, cudaStream_t s);
+
 // mapper self-attention (no mask), S = clip_length + prefix_length small, any head_dim: qkv [B*S, 3d] bf16
 void mapper_attention_fwd(const bf16* qkv, bf16* o, int B, int S, int H, int hd, cudaStream_t s);
 void mapper_attention_bwd(const bf16* qkv, const bf16* d_o, bf16* dqkv, int B, int S, int H, int hd, cudaStream_t s);

@@ -95,7 +95,7 @@ def successor_hot_ids(n_hot: int, text_vocab: int) -> torch.Tensor:
 
 
 def plant_successor_table(w: "OrderedDict[str, torch.Tensor]", cfg: dict, n_hot: int, text_vocab: int, hot_scale: float,
-                          alpha: float, theta: float, kappa: float) -> None:
+                          alpha: float, theta: float, kappa: float, z_ref: float) -> None:
     """Make greedy decoding of the synthetic LM diverse AND numerically well-conditioned (in place).
 
     A random-init GPT-2 has near-Gaussian logits over 50 k tokens: the top-2 margin is a fraction of the logit
@@ -103,19 +103,21 @@ def plant_successor_table(w: "OrderedDict[str, torch.Tensor]", cfg: dict, n_hot:
      -- and scaling a few ``wte`` rows only makes every hot token predict itself.  Here:
 
     * ``n_hot`` seeded ``wte`` rows are scaled by ``hot_scale`` (the candidates);
-    * hidden units ``2j`` and ``2j+1`` of block 0's MLP detect hot token ``j`` at the current position:
-      pre-activations ``z`` and ``z - 1`` with ``z = alpha * <LN2-normalised residual, unit(w_j)> - theta``, so that
-      ``gelu_new(z) - gelu_new(z - 1)`` is a soft 0/1 switch that does not depend on how strongly the token matched;
-    * their ``c_proj`` rows write ``+-(kappa * w_succ(j) - max(kappa, 1.3) * w_j)`` into the residual stream, which the remaining blocks
-      carry to ``ln_f``: the successor's logit gets a structural lead over the best of the other hot rows, while the
-      randomly initialised rest of the network still moves every logit by about one standard deviation, so which
-      margin a step ends up with depends on the whole context (attention, positions, KV history).
+    * hidden unit ``j`` of block 0's MLP detects hot token ``j`` at the current position: its pre-activation is
+      ``z = alpha * <LN2-normalised residual, unit(w_j)> - theta``, at least +6 for the matching token and at most -6 for
+      every other one, so ``gelu_new(z)`` is ~z for a match and ~0 otherwise (no difference of large activations: bf16
+      implementations round ``gelu_new(z)`` to 2^-9 relative, like everything else);
+    * its ``c_proj`` row writes ``kappa * w_succ(j) - max(kappa, 1.3 / z_ref) * w_j`` (per unit of activation) into the
+      residual stream, which the remaining blocks carry to ``ln_f``: the successor's logit gets a structural lead over the
+      best of the other hot rows (the token's own tied-embedding lead is erased), while the randomly initialised rest of
+      the network still moves every logit by about one standard deviation, so which margin a step ends up with depends
+      on the whole context (attention, positions, KV history).
 
-    ``alpha / theta / kappa`` come from ``oracle/calibrate_successor_lm.py`` (probe forwards of this very LM) and are
+    ``alpha / theta / kappa / z_ref`` (``z_ref`` = the matching unit's typical activation) come from ``oracle/calibrate_successor_lm.py`` (probe forwards of this very LM) and are
     recorded as literals in ``oracle/cases.py``: building the weights involves no data-dependent branch.
     """
     d = cfg["d_model"]
-    assert 2 * n_hot <= 4 * d, "the table needs two hidden units per hot token"
+    assert n_hot <= 4 * d, "the table needs one hidden unit per hot token"
     ids = successor_hot_ids(n_hot, text_vocab)
     wte = w["transformer.wte.weight"]
     wte[ids] *= hot_scale
@@ -127,13 +129,9 @@ def plant_successor_table(w: "OrderedDict[str, torch.Tensor]", cfg: dict, n_hot:
     shift = det @ b2                                         # ... and LN2's bias folded into the unit's bias
     fc_w, fc_b = w["transformer.h.0.mlp.c_fc.weight"], w["transformer.h.0.mlp.c_fc.bias"]       # [d, 4d], [4d]
     pr_w = w["transformer.h.0.mlp.c_proj.weight"]                                                  # [4d, d]
-    fc_w[:, 0:2 * n_hot:2] = det.t()
-    fc_w[:, 1:2 * n_hot:2] = det.t()
-    fc_b[0:2 * n_hot:2] = -theta - shift
-    fc_b[1:2 * n_hot:2] = -theta - shift - 1.0
-    write = kappa * succ - max(kappa, 1.3) * hot             # the token's own (tied-embedding) lead is always erased
-    pr_w[0:2 * n_hot:2] = write
-    pr_w[1:2 * n_hot:2] = -write
+    fc_w[:, :n_hot] = det.t()
+    fc_b[:n_hot] = -theta - shift
+    pr_w[:n_hot] = kappa * succ - max(kappa, 1.3 / z_ref) * hot
 
 
 def mapper_param_shapes(mapping_type: str, clip_dim: int, d_model: int, prefix_length: int, clip_length: int,

@@ -2,8 +2,9 @@
 
 Finds, by probe forwards of the oracle on the very LM a case uses, the three constants the planted bigram table needs:
 
-* ``alpha`` / ``theta``: detector gain and threshold such that the matching unit's pre-activation is >= +6 (positions >= 8)
-  and every non-matching one <= -6 on the probe (hot tokens at random positions in random context);
+* ``alpha`` / ``theta`` / ``z_ref``: detector gain and threshold such that the matching unit's pre-activation is >= +6
+  (positions >= 8; ``z_ref`` = its median) and every non-matching one <= -6 on the probe (hot tokens at random positions
+  in random context);
 * ``kappa``: strength of the written ``w_succ - w_tok`` vector such that the successor's logit leads the best other hot
   row by ``target`` logit standard deviations (the std of a hot row's logit is ``|w_hot|``).
 
@@ -54,7 +55,7 @@ def calibrate(model_version, n_hot, text_vocab, hot_scale, vocab=None, target=6.
     cfg = syn.lm_config(model_version, vocab=vocab, n_positions=n_positions)
     ids = syn.successor_hot_ids(n_hot, text_vocab)
     base = dict(n_hot=n_hot, text_vocab=text_vocab, hot_scale=hot_scale)
-    w = syn.make_lm_weights(cfg, seed=0, successor=dict(base, alpha=0.0, theta=0.0, kappa=0.0))
+    w = syn.make_lm_weights(cfg, seed=0, successor=dict(base, alpha=0.0, theta=0.0, kappa=0.0, z_ref=1.0))
     tok, hot_pos = probe_tokens(ids, text_vocab)
     xhat = residual_after_attention0(w, cfg, tok)                                   # [B, T, d]
     hot = w["transformer.wte.weight"][ids]
@@ -67,13 +68,14 @@ def calibrate(model_version, n_hot, text_vocab, hot_scale, vocab=None, target=6.
     assert m_lo > n_hi + 1.0, ("hot tokens are not separable in block 0", m_lo, n_hi)
     alpha = float("%.3g" % (12.0 / (m_lo - n_hi)))
     theta = float("%.3g" % (alpha * (m_lo + n_hi) / 2))
-    print(f"detector: min match {m_lo:.2f}, max non-match (+1.5) {n_hi:.2f} -> alpha {alpha}, theta {theta}")
+    z_ref = float("%.3g" % (alpha * float(G[:, 8:][match[:, 8:]].median()) - theta))     # typical activation of a matching unit
+    print(f"detector: min match {m_lo:.2f}, max non-match (+1.5) {n_hi:.2f} -> alpha {alpha}, theta {theta}, z_ref {z_ref}")
 
     sigma = float(hot.norm(dim=1).mean())        # std of a hot row's logit (ln_f output has norm sqrt(d))
-    kappa = 1.0
+    kappa = 1.0 / z_ref
 
     def lead(kappa):
-        w = syn.make_lm_weights(cfg, seed=0, successor=dict(base, alpha=alpha, theta=theta, kappa=kappa))
+        w = syn.make_lm_weights(cfg, seed=0, successor=dict(base, alpha=alpha, theta=theta, kappa=kappa, z_ref=z_ref))
         hidden = orc.gpt2_hidden(w, w["transformer.wte.weight"][tok], torch.ones_like(tok), cfg["n_layer"], cfg["n_head"])
         sel = hot_pos.clone()
         sel[:, :8] = False
@@ -86,14 +88,14 @@ def calibrate(model_version, n_hot, text_vocab, hot_scale, vocab=None, target=6.
 
     for it in range(4):                          # fixed-point: the structural lead is close to linear in kappa
         m, s = lead(kappa)
-        print(f"kappa {kappa:.3f}: successor logit {float(s.median()):.2f} sigma, lead over the best other hot row median "
+        print(f"kappa {kappa:.4f}: successor logit {float(s.median()):.2f} sigma, lead over the best other hot row median "
               f"{float(m.median()):.2f} / min {float(m.min()):.2f} sigma (sigma = {sigma:.3f})")
         kappa = float("%.3g" % (kappa * target / float(s.median())))
     m, s = lead(kappa)
     print(f"final kappa {kappa}: lead median {float(m.median()):.2f} min {float(m.min()):.2f} sigma; absolute "
           f"{float(m.median()) * sigma:.2f} / {float(m.min()) * sigma:.2f}")
-    print("successor=dict(n_hot=%d, text_vocab=%d, hot_scale=%s, alpha=%s, theta=%s, kappa=%s)"
-          % (n_hot, text_vocab, hot_scale, alpha, theta, kappa))
+    print("successor=dict(n_hot=%d, text_vocab=%d, hot_scale=%s, alpha=%s, theta=%s, kappa=%s, z_ref=%s)"
+          % (n_hot, text_vocab, hot_scale, alpha, theta, kappa, z_ref))
 
 
 if __name__ == "__main__":

@@ -241,6 +241,30 @@ def test_generate_parity(name):
         assert len(got[0]) == len(ref[0])
 
 
+@pytest.mark.parametrize("name", ["gen_tiny_fewshot_chain", "gen_gpt2_prepend_chain", "gen_mini_fewshot_flat"])
+def test_persistent_decode_kernel_equals_the_launch_per_operation_path(name, monkeypatch):
+    """The single-token steps run as ONE cooperative kernel per step (decode_chain.cu: grid barriers between the GEMM /
+    attention / LayerNorm phases).  EAVQA_DECODE_CHAIN=0 selects the older path (one launch per operation, same
+    arithmetic in the same order): tokens, winning logits and picked-token log-probabilities must agree."""
+    case = CASES[name]
+    lm_w, mapper_w, batch, cfg = build_case(case)
+    model = build_model(case, lm_w, mapper_w).eval()
+    kw = dict(question_tokens=batch["input_ids"], prefix=batch["clip_embeddings"], question_mask=batch["attention_mask"],
+              max_length=case["max_length"], pad_token_id=case["pad_token_id"], eos_token_id=None)
+    model.gpt.config.eos_token_id = None
+    monkeypatch.setenv("EAVQA_DECODE_CHAIN", "1")
+    tok1, top1 = model.generate(return_top_logits=True, **kw)
+    _, lp1 = model.generate(return_logprobs=True, **kw)
+    monkeypatch.setenv("EAVQA_DECODE_CHAIN", "0")
+    tok0, top0 = model.generate(return_top_logits=True, **kw)
+    _, lp0 = model.generate(return_logprobs=True, **kw)
+    # split-K partials are added in a different order (fp32 reduce-add): values agree to fp32 round-off of O(10) sums
+    assert (top1 - top0).abs().max().item() <= 2e-3 * (1.0 + top0.abs().max().item())
+    assert (lp1 - lp0).abs().max().item() <= 5e-3
+    agree = sum(int(a == b) for a, b in zip(tok1, tok0))
+    assert agree >= len(tok0) - (0 if case.get("successor") else 1), (tok1, tok0)
+
+
 def test_generate_api_shapes_and_errors():
     case = CASES["gen_tiny_fewshot"]
     lm_w, mapper_w, batch, cfg = build_case(case)
