@@ -12,6 +12,7 @@
 // Data crossing a phase boundary lives in global memory (L2): generic-proxy writers fence towards the async proxy before
 // the barrier, the TMA producer fences after it; bulk stores are waited for (complete, not just read) before the barrier.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "gemm_kernel.cuh"
@@ -36,6 +37,11 @@ constexpr int ATT_GROUP_BYTES = WORK_BYTES / 2;                 // per four-warp
 constexpr int ATT_FIXED = (64 + 4 * 64 + 8) * 4;                // q, per-warp partial outputs, per-warp (max, sum)
 constexpr int HD = 64;
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
@@ -53,9 +59,9 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
 // counter value after every CTA has arrived at this barrier.
 __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned target) {
     fence_proxy_async_all();           // this thread's generic writes -> ordered before later async-proxy (TMA) reads
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();               // cumulative: covers the CTA's writes ordered before it by the barrier above
         atomicAdd(counter, 1u);
         while (static_cast<int>(ld_acquire_gpu(counter) - target) < 0) {
         }
@@ -191,6 +197,11 @@ struct AttGroup {
     int gid, gtid;       // group id in the CTA (0 / 1), thread id in the group (0..127)
 };
 
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// staging layout of one item: K rows [n][64] bf16 | V rows [n][64] bf16 | scores [n] fp32 | key validity [n] int32
 __device__ __forceinline__ void att_issue_loads(const ChainPhase& p, int item, int pos, uint8_t* buf, int gtid) {
     const int b = item / p.H, h = item - b * p.H;
     const bf16* kbase = p.cache + (static_cast<int64_t>(b) * p.H + h) * p.Tmax * HD;
@@ -198,17 +209,42 @@ __device__ __forceinline__ void att_issue_loads(const ChainPhase& p, int item, i
     const int n = pos + 1;
     bf16* Ks = reinterpret_cast<bf16*>(buf);
     bf16* Vs = Ks + static_cast<size_t>(n) * HD;
+    int* vm = reinterpret_cast<int*>(Vs + static_cast<size_t>(n) * HD) + n;
     for (int idx = gtid; idx < pos * 8; idx += 128) {
         const int t = idx >> 3, c = (idx & 7) * 8;
         cp_async_16(ptx::smem_u32(Ks + t * HD + c), kbase + static_cast<int64_t>(t) * HD + c);
         cp_async_16(ptx::smem_u32(Vs + t * HD + c), vbase + static_cast<int64_t>(t) * HD + c);
     }
+    // (a global load of the validity word inside the score loop costs an L2 round trip per four keys)
+    const int* vrow = p.valid + static_cast<int64_t>(b) * p.valid_stride;
+    for (int t = gtid; t < n; t += 128) cp_async_4(ptx::smem_u32(vm + t), vrow + t);
     cp_async_commit();
+}
+
+// this thread's share of an item's new q | k | v row, RAW (accumulator and bias separately: the add happens an item later, so
+// that the in-order issue never waits for these loads): threads 0..63 hold (q, k) of one head dimension, 64..127 hold v
+struct QkvRaw { float a0, b0, a1, b1; };
+__device__ __forceinline__ QkvRaw att_load_qkv(const ChainPhase& p, int item, int gtid) {
+    const int b = item / p.H, h = item - b * p.H;
+    const int d = p.H * HD;
+    const float* __restrict__ arow = p.qkv_acc + static_cast<int64_t>(b) * 3 * d;
+    const float* __restrict__ bias = p.bias;
+    QkvRaw r;
+    if (gtid < HD) {
+        const int c = h * HD + gtid;
+        r.a0 = __ldcg(arow + c); r.b0 = __ldg(bias + c);
+        r.a1 = __ldcg(arow + d + c); r.b1 = __ldg(bias + d + c);
+    } else {
+        const int c = h * HD + gtid - HD;
+        r.a0 = __ldcg(arow + 2 * d + c); r.b0 = __ldg(bias + 2 * d + c);
+        r.a1 = 0.f; r.b1 = 0.f;
+    }
+    return r;
 }
 
 __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, const AttGroup& g) {
     const int n = pos + 1;
-    const int hist_bytes = (2 * n * HD * 2 + n * 4 + 127) & ~127;  // K, V rows + scores (cp.async needs 16-byte aligned rows)
+    const int hist_bytes = (2 * n * HD * 2 + n * 8 + 127) & ~127;  // K, V rows + scores + validity (16-byte aligned rows)
     const bool dbl = 2 * hist_bytes + ATT_FIXED <= ATT_GROUP_BYTES;
     uint8_t* bufs[2] = {g.base, g.base + hist_bytes};
     float* fixed = reinterpret_cast<float*>(g.base + (dbl ? 2 : 1) * hist_bytes);
@@ -222,30 +258,35 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
     const int d = p.H * HD;
     const int bar_id = 1 + g.gid;
 
-    if (first < n_items) att_issue_loads(p, first, pos, bufs[0], g.gtid);
+    QkvRaw cur = {0.f, 0.f, 0.f, 0.f};    // this item's q / k / v element(s), fetched one item ahead
+    if (first < n_items) {
+        att_issue_loads(p, first, pos, bufs[0], g.gtid);
+        cur = att_load_qkv(p, first, g.gtid);
+    }
     int k = 0;
     for (int item = first; item < n_items; item += stride, ++k) {
         uint8_t* buf = bufs[dbl ? (k & 1) : 0];
         const int next = item + stride;
         const bool prefetch = dbl && next < n_items;
         if (prefetch) att_issue_loads(p, next, pos, bufs[(k + 1) & 1], g.gtid);
+        QkvRaw nxt = {0.f, 0.f, 0.f, 0.f};
+        if (next < n_items) nxt = att_load_qkv(p, next, g.gtid);              // latency hidden behind this item's reduction
+        const float a0 = cur.a0 + cur.b0, a1 = cur.a1 + cur.b1;
         const int b = item / p.H, h = item - b * p.H;
         bf16* Ks = reinterpret_cast<bf16*>(buf);
         bf16* Vs = Ks + static_cast<size_t>(n) * HD;
         float* sc = reinterpret_cast<float*>(Vs + static_cast<size_t>(n) * HD);
+        const int* vm = reinterpret_cast<const int*>(sc + n);
         bf16* kbase = p.cache + (static_cast<int64_t>(b) * p.H + h) * p.Tmax * HD;
         bf16* vhead = kbase + static_cast<int64_t>(p.B) * p.H * p.Tmax * HD;
-        const float* arow = p.qkv_acc + static_cast<int64_t>(b) * 3 * d;
         if (g.gtid < HD) {
-            const int c = h * HD + g.gtid;
-            sq[g.gtid] = (__ldcg(arow + c) + __ldg(p.bias + c)) * 0.125f;                      // head_dim ** -0.5 folded into q
-            const bf16 kv = __float2bfloat16(__ldcg(arow + d + c) + __ldg(p.bias + d + c));
+            sq[g.gtid] = a0 * 0.125f;                                              // head_dim ** -0.5 folded into q
+            const bf16 kv = __float2bfloat16(a1);
             kbase[static_cast<int64_t>(pos) * HD + g.gtid] = kv;
             Ks[pos * HD + g.gtid] = kv;
-            if (p.zero != nullptr) p.zero[static_cast<int64_t>(b) * d + c] = 0.f;
+            if (p.zero != nullptr) p.zero[static_cast<int64_t>(b) * d + h * HD + g.gtid] = 0.f;
         } else {
-            const int c = h * HD + g.gtid - HD;
-            const bf16 vv = __float2bfloat16(__ldcg(arow + 2 * d + c) + __ldg(p.bias + 2 * d + c));
+            const bf16 vv = __float2bfloat16(a0);
             vhead[static_cast<int64_t>(pos) * HD + g.gtid - HD] = vv;
             Vs[pos * HD + g.gtid - HD] = vv;
         }
@@ -258,7 +299,6 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
         for (int i = 0; i < 8; ++i) q8[i] = sq[cg * 8 + i];
         const int chunk = (n + 3) >> 2;
         const int t0 = warp * chunk, t1 = min(n, t0 + chunk);
-        const int* vrow = p.valid + static_cast<int64_t>(b) * p.valid_stride;
         for (int tb = t0; tb < t1; tb += 4) {
             const int t = tb + ks;
             const bool ok = t < t1;
@@ -274,7 +314,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
             acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            if (ok && cg == 0) sc[t] = __ldcg(vrow + t) ? acc : -INFINITY;
+            if (ok && cg == 0) sc[t] = vm[t] ? acc : -INFINITY;
         }
         __syncwarp();
         float mx = -INFINITY;
@@ -330,6 +370,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
         }
         named_bar_sync(bar_id, 128);           // sq / part / this buffer are rewritten by the next item
         if (!dbl && next < n_items) att_issue_loads(p, next, pos, bufs[0], g.gtid);
+        cur = nxt;
     }
 }
 
@@ -338,8 +379,15 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
 __device__ __forceinline__ void glue_phase(const ChainPhase& p, int warp, int lane) {
     const int d = p.d, n4 = d >> 2;
     constexpr int MAXV = 16;                  // d <= 2048
-    for (int row = blockIdx.x * (THREADS / 32) + warp; row < p.B; row += gridDim.x * (THREADS / 32)) {
-        float4* xp = reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * d);
+    // rows are dealt round-robin over the CTAs first (one row per SM for up to 148 rows): the phase is a chain of dependent
+    // L2 round trips, so it wants as many SMs as there are rows
+    for (int row = warp * gridDim.x + blockIdx.x; row < p.B; row += gridDim.x * (THREADS / 32)) {
+        float4* __restrict__ xp = reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * d);
+        const float4* __restrict__ ap = p.acc != nullptr ? reinterpret_cast<const float4*>(p.acc + static_cast<size_t>(row) * d) : nullptr;
+        const float4* __restrict__ bp = reinterpret_cast<const float4*>(p.bias);
+        const float4* __restrict__ gp = reinterpret_cast<const float4*>(p.gamma);
+        const float4* __restrict__ tp = reinterpret_cast<const float4*>(p.beta);
+        uint2* __restrict__ up = reinterpret_cast<uint2*>(p.u + static_cast<size_t>(row) * d);
         float4 v[MAXV];
         float sum = 0.f;
 #pragma unroll
@@ -347,9 +395,9 @@ __device__ __forceinline__ void glue_phase(const ChainPhase& p, int warp, int la
             const int c = lane + 32 * i;
             if (c < n4) {
                 v[i] = __ldcg(xp + c);
-                if (p.acc != nullptr) {
-                    const float4 a = __ldcg(reinterpret_cast<const float4*>(p.acc + static_cast<size_t>(row) * d) + c);
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + c);
+                if (ap != nullptr) {
+                    const float4 a = __ldcg(ap + c);
+                    const float4 b = __ldg(bp + c);
                     v[i].x += a.x + b.x; v[i].y += a.y + b.y; v[i].z += a.z + b.z; v[i].w += a.w + b.w;
                     __stcg(xp + c, v[i]);
                 }
@@ -367,28 +415,29 @@ __device__ __forceinline__ void glue_phase(const ChainPhase& p, int warp, int la
             }
         }
         const float rstd = rsqrtf(warp_sum(sq) / d + 1e-5f);
-        uint2* up = reinterpret_cast<uint2*>(p.u + static_cast<size_t>(row) * d);
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             const int c = lane + 32 * i;
             if (c < n4) {
-                const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma) + c), bt = __ldg(reinterpret_cast<const float4*>(p.beta) + c);
+                const float4 gm = __ldg(gp + c), bt = __ldg(tp + c);
                 uint2 o;
                 o.x = pack_bf16x2((v[i].x - mean) * rstd * gm.x + bt.x, (v[i].y - mean) * rstd * gm.y + bt.y);
                 o.y = pack_bf16x2((v[i].z - mean) * rstd * gm.z + bt.z, (v[i].w - mean) * rstd * gm.w + bt.w);
                 __stcg(up + c, o);
             }
         }
-        if (p.zero != nullptr) {
-            float4* zp = reinterpret_cast<float4*>(p.zero + static_cast<size_t>(row) * p.zero_n);
-            for (int c = lane; c < (p.zero_n >> 2); c += 32) __stcg(zp + c, make_float4(0.f, 0.f, 0.f, 0.f));
-        }
+    }
+    if (p.zero != nullptr) {                  // [rows, zero_n] is dense: every thread of the grid clears a few float4
+        float4* zp = reinterpret_cast<float4*>(p.zero);
+        const int total = p.B * (p.zero_n >> 2);
+        for (int i = blockIdx.x * THREADS + threadIdx.x; i < total; i += gridDim.x * THREADS) __stcg(zp + i, make_float4(0.f, 0.f, 0.f, 0.f));
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(THREADS, 1)
-decode_chain_kernel(const ChainPhase* __restrict__ phases, int n_phases, int pos, unsigned* bar_counter, unsigned epoch0) {
+decode_chain_kernel(const ChainPhase* __restrict__ phases, int n_phases, int pos, unsigned* bar_counter, unsigned epoch0,
+                    unsigned long long* trace) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -432,6 +481,7 @@ decode_chain_kernel(const ChainPhase* __restrict__ phases, int n_phases, int pos
     grp.base = smem + grp.gid * ATT_GROUP_BYTES;
     const unsigned G = gridDim.x;
 
+    if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) trace[0] = globaltimer_ns();
     for (int ph = 0; ph < n_phases; ++ph) {
         const ChainPhase& p = phases[ph];
         if (p.type == CHAIN_GEMM) {
@@ -447,7 +497,14 @@ decode_chain_kernel(const ChainPhase* __restrict__ phases, int n_phases, int pos
         } else {
             glue_phase(p, warp, lane);
         }
+        if (threadIdx.x < 3 && ph + 1 < n_phases && phases[ph + 1].type == CHAIN_GEMM) {
+            // the TMA unit fetches a descriptor from global memory on first use: start that before the barrier
+            const ChainPhase& nx = phases[ph + 1];
+            ptx::prefetch_tensormap(threadIdx.x == 0 ? &nx.map_a : threadIdx.x == 1 ? &nx.map_b : &nx.map_out);
+        }
+        if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) trace[1 + 2 * ph] = globaltimer_ns();      // CTA 0's own work done
         grid_sync(bar_counter, (epoch0 + static_cast<unsigned>(ph) + 1u) * G);
+        if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) trace[2 + 2 * ph] = globaltimer_ns();      // everyone's work done
     }
 
     ptx::tcgen05_fence_before();
@@ -465,7 +522,7 @@ static_assert(sizeof(ChainPhase) % 128 == 0, "tensor maps inside an array of pha
 
 bool decode_chain_supported(int max_keys) {
     // the attention phases stage one head's whole K / V history per four-warp group
-    return ((2 * max_keys * dc::HD * 2 + max_keys * 4 + 127) & ~127) + dc::ATT_FIXED <= dc::ATT_GROUP_BYTES;
+    return ((2 * max_keys * dc::HD * 2 + max_keys * 8 + 127) & ~127) + dc::ATT_FIXED <= dc::ATT_GROUP_BYTES;
 }
 
 void chain_gemm_phase(ChainPhase& p, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, int split, int mode, void* out,
@@ -502,7 +559,8 @@ void chain_glue_phase(ChainPhase& p, float* x, const float* acc, const float* bi
     p.x = x; p.acc = acc; p.bias = bias; p.gamma = gamma; p.beta = beta; p.u = u; p.B = rows; p.d = d; p.zero = zero; p.zero_n = zero_n;
 }
 
-void launch_decode_chain(const ChainPhase* dev_phases, int n_phases, int pos, unsigned* bar_counter, unsigned epoch0, cudaStream_t s) {
+void launch_decode_chain(const ChainPhase* dev_phases, int n_phases, int pos, unsigned* bar_counter, unsigned epoch0, cudaStream_t s,
+                         unsigned long long* trace) {
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(dc::decode_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::SMEM));
@@ -518,7 +576,7 @@ void launch_decode_chain(const ChainPhase* dev_phases, int n_phases, int pos, un
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, dc::decode_chain_kernel, dev_phases, n_phases, pos, bar_counter, epoch0));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, dc::decode_chain_kernel, dev_phases, n_phases, pos, bar_counter, epoch0, trace));
     KERNEL_CHECK();
     count_launch();
 }

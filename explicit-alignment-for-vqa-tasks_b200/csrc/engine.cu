@@ -748,9 +748,11 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     const char* chain_opt = getenv("EAVQA_DECODE_CHAIN");
     const bool chain_env = !(chain_opt != nullptr && chain_opt[0] == '0');
     const bool use_chain = chain_env && max_new > 1 && B <= 128 && d % 64 == 0 && decode_chain_supported(Tmax);
-    const int n_chain = 2 + 7 * L;
+    const int n_chain = 1 + 7 * L;
     ChainPhase* chain_dev = nullptr;
     unsigned* chain_bar = nullptr;
+    unsigned long long* chain_trace = nullptr;
+    const bool trace_on = getenv("EAVQA_CHAIN_TRACE") != nullptr;     // per-phase timing of the last step, printed to stderr
     auto plan_all = [&](Arena& a) {
         const size_t m = static_cast<size_t>(M);
         mw.plan(a, *this, false);
@@ -771,6 +773,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         kv = a.get<bf16>(kv_layer * L);
         chain_dev = a.get<ChainPhase>(n_chain);
         chain_bar = a.get<unsigned>(1);
+        chain_trace = a.get<unsigned long long>(1 + 2 * n_chain);
     };
     {
         arena_.begin_measure();
@@ -857,14 +860,16 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
             else
                 chain_glue_phase(ph[k++], x_a, acc_pr, w.b_pr, lnf_g_, lnf_b_, hc, B, d, nullptr, 0);
         }
-        chain_gemm_phase(ph[k++], hc, d, wte_bf16_, d, B, Vpad_, d, 1, CHAIN_STORE_F32, logits, Vpad_, nullptr);
         EAVQA_CHECK(k == n_chain, "decode chain phase count");
         CUDA_CHECK(cudaMemcpyAsync(chain_dev, ph.data(), sizeof(ChainPhase) * n_chain, cudaMemcpyHostToDevice, s));
         fill_zero(chain_bar, sizeof(unsigned), s);
         unsigned epoch = 0;
         for (int step = 1; step < max_new; ++step) {
-            launch_decode_chain(chain_dev, n_chain, T0 + step - 1, chain_bar, epoch, s);
+            launch_decode_chain(chain_dev, n_chain, T0 + step - 1, chain_bar, epoch, s, trace_on ? chain_trace : nullptr);
             epoch += static_cast<unsigned>(n_chain);
+            // the head (B x Vpad x d, 100 MB of weights) runs on the wide-tile stand-alone GEMM: at 64-column tiles the chain
+            // would re-read the 128 activation rows once per tile (measured 36 us against ~20)
+            gemm(hc, d, wte_bf16_, d, B, Vpad_, d, ep_f32(logits, Vpad_), s);
             greedy_step(logits, Vpad_, B, V_, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out, n_unfinished, top_logit,
                         token_logprob, wte_f32_, wpe_f32_ + static_cast<size_t>(std::min(T0 + step, cfg_.n_positions - 1)) * d, d, x_a,
                         validD + T0 + step, Tmax, part_val, part_idx, arrivals, s);
@@ -902,6 +907,26 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         fprintf(stderr, "[eavqa] generate: host enqueue %.3f ms, then waited %.3f ms for the GPU\n",
                 std::chrono::duration<double, std::milli>(t_enq - t_begin).count(),
                 std::chrono::duration<double, std::milli>(t_end - t_enq).count());
+    }
+    if (use_chain && trace_on) {
+        std::vector<unsigned long long> t(1 + 2 * n_chain);
+        CUDA_CHECK(cudaMemcpy(t.data(), chain_trace, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
+        double work[3] = {0, 0, 0}, wait[3] = {0, 0, 0};
+        int cnt[3] = {0, 0, 0};
+        std::vector<ChainPhase> ph(n_chain);
+        CUDA_CHECK(cudaMemcpy(ph.data(), chain_dev, sizeof(ChainPhase) * n_chain, cudaMemcpyDeviceToHost));
+        double by_shape[8] = {0};
+        for (int i = 0; i < n_chain; ++i) {
+            const unsigned long long begin = i == 0 ? t[0] : t[2 * i], own = t[1 + 2 * i], all = t[2 + 2 * i];
+            work[ph[i].type] += static_cast<double>(own - begin) * 1e-3;
+            wait[ph[i].type] += static_cast<double>(all - own) * 1e-3;
+            cnt[ph[i].type]++;
+            if (ph[i].type == CHAIN_GEMM) by_shape[(i - 1) % 7] += static_cast<double>(all - begin) * 1e-3;
+        }
+        fprintf(stderr, "[eavqa] decode chain, last step: %.1f us total; per phase (CTA 0 work + wait at barrier, us): gemm %.2f + %.2f (x%d), "
+                        "attention %.2f + %.2f (x%d), glue %.2f + %.2f (x%d); gemm phases per layer: qkv %.2f o %.2f fc %.2f pr %.2f\n",
+                static_cast<double>(t[2 * n_chain] - t[0]) * 1e-3, work[0] / cnt[0], wait[0] / cnt[0], cnt[0], work[1] / cnt[1], wait[1] / cnt[1],
+                cnt[1], work[2] / cnt[2], wait[2] / cnt[2], cnt[2], by_shape[0] / L, by_shape[2] / L, by_shape[4] / L, by_shape[5] / L);
     }
     EAVQA_CHECK(host_flags_[max_new] == 0,
                 "prompt rows must each hold exactly n_images sentinel tokens (vct0.py:512 would fail its .view)");

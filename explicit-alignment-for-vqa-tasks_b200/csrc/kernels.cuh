@@ -165,7 +165,9 @@ void chain_attn_phase(ChainPhase& p, const float* qkv_acc, const float* qkv_bias
 void chain_glue_phase(ChainPhase& p, float* x, const float* acc, const float* bias, const float* gamma, const float* beta, bf16* u, int rows,
                       int d, float* zero, int zero_n);
 // bar_counter: device counter zeroed once per generate call; epoch0 = grid barriers executed by earlier launches since then
-void launch_decode_chain(const ChainPhase* dev_phases, int n_phases, int pos, unsigned* bar_counter, unsigned epoch0, cudaStream_t s);
+// trace (optional, EAVQA_CHAIN_TRACE=1): [1 + 2 n_phases] globaltimer stamps of CTA 0 -- start, then per phase (own work done, barrier passed)
+void launch_decode_chain(const ChainPhase* dev_phases, int n_phases, int pos, unsigned* bar_counter, unsigned epoch0, cudaStream_t s,
+                         unsigned long long* trace = nullptr);
 
 // mapper self-attention (no mask), S = clip_length + prefix_length small, any head_dim: qkv [B*S, 3d] bf16
 void mapper_attention_fwd(const bf16* qkv, bf16* o, int B, int S, int H, int hd, cudaStream_t s);
