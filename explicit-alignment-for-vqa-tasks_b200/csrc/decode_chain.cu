@@ -242,7 +242,11 @@ __device__ __forceinline__ QkvRaw att_load_qkv(const ChainPhase& p, int item, in
     return r;
 }
 
-__device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, const AttGroup& g) {
+#define ATT_T(i) do { if (dbg != nullptr) { const long long now_ = clock64(); seg[i] += now_ - tprev; tprev = now_; } } while (0)
+__device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, const AttGroup& g, unsigned long long* dbg_in) {
+    unsigned long long* dbg = (blockIdx.x == 0 && g.gid == 0 && g.gtid == 0) ? dbg_in : nullptr;
+    long long seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
     const int n = pos + 1;
     const int hist_bytes = (2 * n * HD * 2 + n * 8 + 127) & ~127;  // K, V rows + scores + validity (16-byte aligned rows)
     const bool dbl = 2 * hist_bytes + ATT_FIXED <= ATT_GROUP_BYTES;
@@ -271,6 +275,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
         if (prefetch) att_issue_loads(p, next, pos, bufs[(k + 1) & 1], g.gtid);
         QkvRaw nxt = {0.f, 0.f, 0.f, 0.f};
         if (next < n_items) nxt = att_load_qkv(p, next, g.gtid);              // latency hidden behind this item's reduction
+        ATT_T(0);
         const float a0 = cur.a0 + cur.b0, a1 = cur.a1 + cur.b1;
         const int b = item / p.H, h = item - b * p.H;
         bf16* Ks = reinterpret_cast<bf16*>(buf);
@@ -292,7 +297,9 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
         }
         if (prefetch) cp_async_wait_group<1>();
         else cp_async_wait_group<0>();
+        ATT_T(1);
         named_bar_sync(bar_id, 128);
+        ATT_T(2);
         const int ks = lane >> 3, cg = lane & 7;
         float q8[8];
 #pragma unroll
@@ -317,6 +324,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
             if (ok && cg == 0) sc[t] = vm[t] ? acc : -INFINITY;
         }
         __syncwarp();
+        ATT_T(3);
         float mx = -INFINITY;
         for (int t = t0 + lane; t < t1; t += 32) mx = fmaxf(mx, sc[t]);
         mx = warp_max(mx);
@@ -329,6 +337,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
         }
         sum = warp_sum(sum);
         __syncwarp();
+        ATT_T(4);
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -354,6 +363,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
             part_m[warp] = mx;
             part_l[warp] = sum;
         }
+        ATT_T(5);
         named_bar_sync(bar_id, 128);
         if (g.gtid < HD) {
             const float m = fmaxf(fmaxf(part_m[0], part_m[1]), fmaxf(part_m[2], part_m[3]));
@@ -371,6 +381,11 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
         named_bar_sync(bar_id, 128);           // sq / part / this buffer are rewritten by the next item
         if (!dbl && next < n_items) att_issue_loads(p, next, pos, bufs[0], g.gtid);
         cur = nxt;
+        ATT_T(6);
+    }
+    if (dbg != nullptr) {
+        for (int i = 0; i < 7; ++i) dbg[i] = static_cast<unsigned long long>(seg[i]);
+        dbg[7] = static_cast<unsigned long long>(k);
     }
 }
 
@@ -493,7 +508,7 @@ decode_chain_kernel(const ChainPhase* __restrict__ phases, int n_phases, int pos
                 gemm_epilogue(p, accs, tfull_bar, tempty_bar, tmem_base, smem_epi + (warp - 2) * EPI_BUF, warp, lane);
             }
         } else if (p.type == CHAIN_ATTN) {
-            if (warp >= 2) attention_phase(p, pos, grp);
+            if (warp >= 2) attention_phase(p, pos, grp, trace != nullptr ? trace + 1 + 2 * n_phases : nullptr);
         } else {
             glue_phase(p, warp, lane);
         }

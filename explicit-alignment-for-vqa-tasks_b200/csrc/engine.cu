@@ -773,7 +773,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         kv = a.get<bf16>(kv_layer * L);
         chain_dev = a.get<ChainPhase>(n_chain);
         chain_bar = a.get<unsigned>(1);
-        chain_trace = a.get<unsigned long long>(1 + 2 * n_chain);
+        chain_trace = a.get<unsigned long long>(9 + 2 * n_chain);
     };
     {
         arena_.begin_measure();
@@ -909,7 +909,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
                 std::chrono::duration<double, std::milli>(t_end - t_enq).count());
     }
     if (use_chain && trace_on) {
-        std::vector<unsigned long long> t(1 + 2 * n_chain);
+        std::vector<unsigned long long> t(9 + 2 * n_chain);
         CUDA_CHECK(cudaMemcpy(t.data(), chain_trace, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
         double work[3] = {0, 0, 0}, wait[3] = {0, 0, 0};
         int cnt[3] = {0, 0, 0};
@@ -922,6 +922,12 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
             wait[ph[i].type] += static_cast<double>(all - own) * 1e-3;
             cnt[ph[i].type]++;
             if (ph[i].type == CHAIN_GEMM) by_shape[(i - 1) % 7] += static_cast<double>(all - begin) * 1e-3;
+        }
+        {
+            const unsigned long long* a = t.data() + 1 + 2 * n_chain;
+            fprintf(stderr, "[eavqa] attention phase, last layer, group 0 of CTA 0, %llu items, cycles per item: issue next %llu, write q/k/v + wait loads %llu, "
+                            "barrier %llu, scores %llu, softmax %llu, PV %llu, merge + 2 barriers %llu\n", a[7], a[0] / a[7], a[1] / a[7], a[2] / a[7],
+                    a[3] / a[7], a[4] / a[7], a[5] / a[7], a[6] / a[7]);
         }
         fprintf(stderr, "[eavqa] decode chain, last step: %.1f us total; per phase (CTA 0 work + wait at barrier, us): gemm %.2f + %.2f (x%d), "
                         "attention %.2f + %.2f (x%d), glue %.2f + %.2f (x%d); gemm phases per layer: qkv %.2f o %.2f fc %.2f pr %.2f\n",
