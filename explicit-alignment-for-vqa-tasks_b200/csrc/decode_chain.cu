@@ -36,6 +36,7 @@ constexpr int TMEM_COLS = 128;                                  // two 64-column
 constexpr int ATT_GROUP_BYTES = WORK_BYTES / 2;                 // per four-warp group
 constexpr int ATT_FIXED = (64 + 4 * 64 + 8) * 4;                // q, per-warp partial outputs, per-warp (max, sum)
 constexpr int HD = 64;
+constexpr int ATT_BAR_OFS = 160;                                // four mbarriers (two groups x two buffers) inside the barrier block
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -195,14 +196,23 @@ __device__ __forceinline__ void gemm_epilogue(const ChainPhase& p, AccState& as,
 struct AttGroup {
     uint8_t* base;       // this group's staging area
     int gid, gtid;       // group id in the CTA (0 / 1), thread id in the group (0..127)
+    uint32_t bar[2];     // mbarriers of the two staging buffers (bulk-copy completion)
+    uint32_t parity[2];  // their current phase parities (persist across the attention phases of the kernel)
 };
 
 __device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): one instruction per contiguous history instead of one LDGSTS per
+// 512 bytes (measured: the 144 cp.async warp-instructions of an item kept the LSU busy for ~2800 cycles per item)
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // staging layout of one item: K rows [n][64] bf16 | V rows [n][64] bf16 | scores [n] fp32 | key validity [n] int32
-__device__ __forceinline__ void att_issue_loads(const ChainPhase& p, int item, int pos, uint8_t* buf, int gtid) {
+__device__ __forceinline__ void att_issue_loads(const ChainPhase& p, int item, int pos, uint8_t* buf, int gtid, uint32_t bar) {
     const int b = item / p.H, h = item - b * p.H;
     const bf16* kbase = p.cache + (static_cast<int64_t>(b) * p.H + h) * p.Tmax * HD;
     const bf16* vbase = kbase + static_cast<int64_t>(p.B) * p.H * p.Tmax * HD;
@@ -210,10 +220,13 @@ __device__ __forceinline__ void att_issue_loads(const ChainPhase& p, int item, i
     bf16* Ks = reinterpret_cast<bf16*>(buf);
     bf16* Vs = Ks + static_cast<size_t>(n) * HD;
     int* vm = reinterpret_cast<int*>(Vs + static_cast<size_t>(n) * HD) + n;
-    for (int idx = gtid; idx < pos * 8; idx += 128) {
-        const int t = idx >> 3, c = (idx & 7) * 8;
-        cp_async_16(ptx::smem_u32(Ks + t * HD + c), kbase + static_cast<int64_t>(t) * HD + c);
-        cp_async_16(ptx::smem_u32(Vs + t * HD + c), vbase + static_cast<int64_t>(t) * HD + c);
+    if (gtid == 0 && pos > 0) {
+        // the buffer was last READ through the generic proxy (the item two back): order those reads before the async writes
+        ptx::fence_proxy_async_smem();
+        const uint32_t bytes = static_cast<uint32_t>(pos) * HD * 2;
+        ptx::mbar_arrive_expect_tx(bar, 2 * bytes);
+        bulk_copy_g2s(ptx::smem_u32(Ks), kbase, bytes, bar);
+        bulk_copy_g2s(ptx::smem_u32(Vs), vbase, bytes, bar);
     }
     // (a global load of the validity word inside the score loop costs an L2 round trip per four keys)
     const int* vrow = p.valid + static_cast<int64_t>(b) * p.valid_stride;
@@ -243,7 +256,7 @@ __device__ __forceinline__ QkvRaw att_load_qkv(const ChainPhase& p, int item, in
 }
 
 #define ATT_T(i) do { if (dbg != nullptr) { const long long now_ = clock64(); seg[i] += now_ - tprev; tprev = now_; } } while (0)
-__device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, const AttGroup& g, unsigned long long* dbg_in) {
+__device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, AttGroup& g, unsigned long long* dbg_in) {
     unsigned long long* dbg = (blockIdx.x == 0 && g.gid == 0 && g.gtid == 0) ? dbg_in : nullptr;
     long long seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
@@ -264,7 +277,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
 
     QkvRaw cur = {0.f, 0.f, 0.f, 0.f};    // this item's q / k / v element(s), fetched one item ahead
     if (first < n_items) {
-        att_issue_loads(p, first, pos, bufs[0], g.gtid);
+        att_issue_loads(p, first, pos, bufs[0], g.gtid, g.bar[0]);
         cur = att_load_qkv(p, first, g.gtid);
     }
     int k = 0;
@@ -272,7 +285,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
         uint8_t* buf = bufs[dbl ? (k & 1) : 0];
         const int next = item + stride;
         const bool prefetch = dbl && next < n_items;
-        if (prefetch) att_issue_loads(p, next, pos, bufs[(k + 1) & 1], g.gtid);
+        if (prefetch) att_issue_loads(p, next, pos, bufs[(k + 1) & 1], g.gtid, g.bar[(k + 1) & 1]);
         QkvRaw nxt = {0.f, 0.f, 0.f, 0.f};
         if (next < n_items) nxt = att_load_qkv(p, next, g.gtid);              // latency hidden behind this item's reduction
         ATT_T(0);
@@ -295,8 +308,13 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
             vhead[static_cast<int64_t>(pos) * HD + g.gtid - HD] = vv;
             Vs[pos * HD + g.gtid - HD] = vv;
         }
-        if (prefetch) cp_async_wait_group<1>();
+        if (prefetch) cp_async_wait_group<1>();        // (the validity words still travel by cp.async)
         else cp_async_wait_group<0>();
+        if (pos > 0) {
+            const int bi = dbl ? (k & 1) : 0;
+            ptx::mbar_wait(g.bar[bi], g.parity[bi]);
+            g.parity[bi] ^= 1;
+        }
         ATT_T(1);
         named_bar_sync(bar_id, 128);
         ATT_T(2);
@@ -306,6 +324,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
         for (int i = 0; i < 8; ++i) q8[i] = sq[cg * 8 + i];
         const int chunk = (n + 3) >> 2;
         const int t0 = warp * chunk, t1 = min(n, t0 + chunk);
+#pragma unroll 3
         for (int tb = t0; tb < t1; tb += 4) {
             const int t = tb + ks;
             const bool ok = t < t1;
@@ -341,6 +360,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 3
         for (int t = t0 + ks; t < t1; t += 4) {
             const float pr = sc[t];
             const uint4 u = *reinterpret_cast<const uint4*>(Vs + t * HD + cg * 8);
@@ -379,7 +399,7 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, co
             p.o[static_cast<int64_t>(b) * d + h * HD + g.gtid] = __float2bfloat16(l > 0.f ? v / l : 0.f);
         }
         named_bar_sync(bar_id, 128);           // sq / part / this buffer are rewritten by the next item
-        if (!dbl && next < n_items) att_issue_loads(p, next, pos, bufs[0], g.gtid);
+        if (!dbl && next < n_items) att_issue_loads(p, next, pos, bufs[0], g.gtid, g.bar[0]);
         cur = nxt;
         ATT_T(6);
     }
@@ -475,6 +495,7 @@ decode_chain_kernel(const ChainPhase* __restrict__ phases, int n_phases, int pos
             ptx::mbar_init(tfull_bar + 8 * i, 1);
             ptx::mbar_init(tempty_bar + 8 * i, EPI_WARPS);
         }
+        for (int i = 0; i < 4; ++i) ptx::mbar_init(bars + ATT_BAR_OFS + 8 * i, 1);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async_smem();
     }
@@ -494,6 +515,9 @@ decode_chain_kernel(const ChainPhase* __restrict__ phases, int n_phases, int pos
     grp.gid = warp >= 6 ? 1 : 0;
     grp.gtid = (threadIdx.x - 64) & 127;
     grp.base = smem + grp.gid * ATT_GROUP_BYTES;
+    grp.bar[0] = bars + ATT_BAR_OFS + 16 * grp.gid;
+    grp.bar[1] = grp.bar[0] + 8;
+    grp.parity[0] = grp.parity[1] = 0;
     const unsigned G = gridDim.x;
 
     if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) trace[0] = globaltimer_ns();
