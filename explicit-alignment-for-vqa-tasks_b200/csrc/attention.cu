@@ -735,6 +735,8 @@ __global__ void __launch_bounds__(128) lm_attention_decode_staged_kernel(const f
     bf16* Ks = reinterpret_cast<bf16*>(smem_dec);            // [n][64]
     bf16* Vs = Ks + static_cast<size_t>(n) * HD;             // [n][64]
     float* sc = reinterpret_cast<float*>(Vs + static_cast<size_t>(n) * HD);      // [n]
+    int* vm = reinterpret_cast<int*>(sc + n);                // [n] key validity (a global load inside the score loop costs an
+                                                             // L1-missing round trip per 32 keys on the critical path)
     __shared__ __align__(16) float sq[HD];
     __shared__ float part[4][HD];
     __shared__ float part_m[4], part_l[4];
@@ -745,12 +747,21 @@ __global__ void __launch_bounds__(128) lm_attention_decode_staged_kernel(const f
     const int B = gridDim.x / H;
     bf16* kbase = cache + (static_cast<int64_t>(b) * H + h) * Tmax * HD;
     bf16* vhead = kbase + static_cast<int64_t>(B) * H * Tmax * HD;
-    // history: 2 * pos rows of 128 B = 8 x 16-B requests each
+    // history: 2 * pos rows of 128 B = 8 x 16-B requests each.  Two cp.async groups: the keys (+ validity words) first, so that
+    // the scores and the softmax run while the values are still streaming in (round-2 ncu: DRAM busy only 36 % of the kernel,
+    // every CTA of a wave loaded, then computed, in lock-step)
     for (int idx = tid; idx < pos * 8; idx += 128) {
         const int t = idx >> 3, c = (idx & 7) * 8;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(Ks + t * HD + c)), "l"(kbase + static_cast<int64_t>(t) * HD + c) : "memory");
+    }
+    for (int t = tid; t < n; t += 128)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(vm + t)), "l"(valid + static_cast<int64_t>(b) * valid_stride + t) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int idx = tid; idx < pos * 8; idx += 128) {
+        const int t = idx >> 3, c = (idx & 7) * 8;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(Vs + t * HD + c)), "l"(vhead + static_cast<int64_t>(t) * HD + c) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // this step's q / k / v from the fp32 accumulators: k, v go to the cache AND to their shared-memory rows
     if (tid < HD) {
         const int c = h * HD + tid;
@@ -765,7 +776,7 @@ __global__ void __launch_bounds__(128) lm_attention_decode_staged_kernel(const f
         vhead[static_cast<int64_t>(pos) * HD + tid - HD] = vv;
         Vs[pos * HD + tid - HD] = vv;
     }
-    cp_async_wait_all();
+    asm volatile("cp.async.wait_group 1;" ::: "memory");        // keys + validity have landed
     __syncthreads();
     // lane = (key slot ks, 16-byte column group cg): 8 lanes read one 128-byte row (conflict-free), 4 keys per warp pass
     const int ks = lane >> 3, cg = lane & 7;
@@ -789,7 +800,7 @@ __global__ void __launch_bounds__(128) lm_attention_decode_staged_kernel(const f
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (ok && cg == 0) sc[t] = valid[static_cast<int64_t>(b) * valid_stride + t] ? acc : -INFINITY;
+        if (ok && cg == 0) sc[t] = vm[t] ? acc : -INFINITY;
     }
     __syncwarp();
     float mx = -INFINITY;
@@ -803,7 +814,8 @@ __global__ void __launch_bounds__(128) lm_attention_decode_staged_kernel(const f
         sum += p;
     }
     sum = warp_sum(sum);
-    __syncwarp();
+    cp_async_wait_all();                                        // the values
+    __syncthreads();
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -1283,11 +1295,11 @@ void lm_attention_decode_acc(const float* qkv_acc, const float* qkv_bias, bf16* 
     EAVQA_CHECK(pos < Tmax, "decode position beyond the KV cache");
     const int n = pos + 1;
     if (n <= kDecodeStageKeys) {
-        const size_t smem = static_cast<size_t>(n) * (2 * HD * sizeof(bf16) + sizeof(float));
+        const size_t smem = static_cast<size_t>(n) * (2 * HD * sizeof(bf16) + sizeof(float) + sizeof(int));
         static bool configured = false;
         if (!configured) {
             CUDA_CHECK(cudaFuncSetAttribute(lm_attention_decode_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            kDecodeStageKeys * (2 * HD * static_cast<int>(sizeof(bf16)) + static_cast<int>(sizeof(float)))));
+                                            kDecodeStageKeys * (2 * HD * static_cast<int>(sizeof(bf16)) + 2 * static_cast<int>(sizeof(float)))));
             configured = true;
         }
         launch_kernel(lm_attention_decode_staged_kernel, dim3(B * H), dim3(128), smem, s, qkv_acc, qkv_bias, cache, valid, valid_stride, o,

@@ -30,13 +30,14 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_BUF = 4096;                                   // 32 rows x 128 B (fp32) or 32 x 64 B (bf16)
 constexpr int PIPE_BYTES = STAGES * (STAGE_A + STAGE_B);        // 147456
 constexpr int WORK_BYTES = PIPE_BYTES + EPI_WARPS * EPI_BUF;    // 180224: also the attention phases' staging area
-constexpr int BAR_BYTES = 256;
+constexpr int BAR_BYTES = 512;
 constexpr int SMEM = WORK_BYTES + BAR_BYTES + 1024;
 constexpr int TMEM_COLS = 128;                                  // two 64-column fp32 accumulators
 constexpr int ATT_GROUP_BYTES = WORK_BYTES / 2;                 // per four-warp group
 constexpr int ATT_FIXED = (64 + 4 * 64 + 8) * 4;                // q, per-warp partial outputs, per-warp (max, sum)
 constexpr int HD = 64;
 constexpr int ATT_BAR_OFS = 160;                                // four mbarriers (two groups x two buffers) inside the barrier block
+constexpr int GLUE_RED_OFS = 256;                               // 32 floats of reduction scratch for the glue phases
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -411,56 +412,80 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, At
 
 // ---------------------------------------------------------------------------------------------------------- glue phase
 // x[row] += acc[row] + bias (when acc != null); u[row] = LN(x[row]) * gamma + beta (bf16); zero[row, 0..zero_n) = 0.  One row per warp.
-__device__ __forceinline__ void glue_phase(const ChainPhase& p, int warp, int lane) {
+// One row per CTA at a time, spread over all 320 threads (<= 2 float4 each): every global load of the row -- x, accumulator,
+// bias, gamma, beta -- is in flight at once and the two reductions go through shared memory, so the phase costs about one L2
+// round trip.  (First version: one row per warp, 8 float4 per lane with the dependent store of each vector between the loads
+// of the next -- in-order issue serialised the round trips: 9 us per phase.)
+__device__ __forceinline__ void glue_phase(const ChainPhase& p, int warp, int lane, float* red) {
     const int d = p.d, n4 = d >> 2;
-    constexpr int MAXV = 16;                  // d <= 2048
-    // rows are dealt round-robin over the CTAs first (one row per SM for up to 148 rows): the phase is a chain of dependent
-    // L2 round trips, so it wants as many SMs as there are rows
-    for (int row = warp * gridDim.x + blockIdx.x; row < p.B; row += gridDim.x * (THREADS / 32)) {
+    const int tid = threadIdx.x;
+    for (int row = blockIdx.x; row < p.B; row += gridDim.x) {
         float4* __restrict__ xp = reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * d);
         const float4* __restrict__ ap = p.acc != nullptr ? reinterpret_cast<const float4*>(p.acc + static_cast<size_t>(row) * d) : nullptr;
         const float4* __restrict__ bp = reinterpret_cast<const float4*>(p.bias);
         const float4* __restrict__ gp = reinterpret_cast<const float4*>(p.gamma);
         const float4* __restrict__ tp = reinterpret_cast<const float4*>(p.beta);
         uint2* __restrict__ up = reinterpret_cast<uint2*>(p.u + static_cast<size_t>(row) * d);
-        float4 v[MAXV];
+        float4 v[2], a[2], b[2], gm[2], bt[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = tid + THREADS * j;
+            if (c < n4) {
+                v[j] = __ldcg(xp + c);
+                if (ap != nullptr) {
+                    a[j] = __ldcg(ap + c);
+                    b[j] = __ldg(bp + c);
+                }
+                gm[j] = __ldg(gp + c);
+                bt[j] = __ldg(tp + c);
+            }
+        }
         float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int c = lane + 32 * i;
+        for (int j = 0; j < 2; ++j) {
+            const int c = tid + THREADS * j;
             if (c < n4) {
-                v[i] = __ldcg(xp + c);
                 if (ap != nullptr) {
-                    const float4 a = __ldcg(ap + c);
-                    const float4 b = __ldg(bp + c);
-                    v[i].x += a.x + b.x; v[i].y += a.y + b.y; v[i].z += a.z + b.z; v[i].w += a.w + b.w;
-                    __stcg(xp + c, v[i]);
+                    v[j].x += a[j].x + b[j].x; v[j].y += a[j].y + b[j].y; v[j].z += a[j].z + b[j].z; v[j].w += a[j].w + b[j].w;
+                    __stcg(xp + c, v[j]);
                 }
-                sum += v[i].x + v[i].y + v[i].z + v[i].w;
+                sum += v[j].x + v[j].y + v[j].z + v[j].w;
             }
         }
-        const float mean = warp_sum(sum) / d;
+        sum = warp_sum(sum);
+        if (lane == 0) red[warp] = sum;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) tot += red[w];
+        const float mean = tot / d;
         float sq = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int c = lane + 32 * i;
+        for (int j = 0; j < 2; ++j) {
+            const int c = tid + THREADS * j;
             if (c < n4) {
-                const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
-                sq += a * a + b * b + e * e + f * f;
+                const float e0 = v[j].x - mean, e1 = v[j].y - mean, e2 = v[j].z - mean, e3 = v[j].w - mean;
+                sq += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
             }
         }
-        const float rstd = rsqrtf(warp_sum(sq) / d + 1e-5f);
+        sq = warp_sum(sq);
+        if (lane == 0) red[16 + warp] = sq;
+        __syncthreads();
+        float tot2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int c = lane + 32 * i;
+        for (int w = 0; w < THREADS / 32; ++w) tot2 += red[16 + w];
+        const float rstd = rsqrtf(tot2 / d + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = tid + THREADS * j;
             if (c < n4) {
-                const float4 gm = __ldg(gp + c), bt = __ldg(tp + c);
                 uint2 o;
-                o.x = pack_bf16x2((v[i].x - mean) * rstd * gm.x + bt.x, (v[i].y - mean) * rstd * gm.y + bt.y);
-                o.y = pack_bf16x2((v[i].z - mean) * rstd * gm.z + bt.z, (v[i].w - mean) * rstd * gm.w + bt.w);
+                o.x = pack_bf16x2((v[j].x - mean) * rstd * gm[j].x + bt[j].x, (v[j].y - mean) * rstd * gm[j].y + bt[j].y);
+                o.y = pack_bf16x2((v[j].z - mean) * rstd * gm[j].z + bt[j].z, (v[j].w - mean) * rstd * gm[j].w + bt[j].w);
                 __stcg(up + c, o);
             }
         }
+        __syncthreads();                      // `red` is rewritten by the next row
     }
     if (p.zero != nullptr) {                  // [rows, zero_n] is dense: every thread of the grid clears a few float4
         float4* zp = reinterpret_cast<float4*>(p.zero);
@@ -534,7 +559,7 @@ decode_chain_kernel(const ChainPhase* __restrict__ phases, int n_phases, int pos
         } else if (p.type == CHAIN_ATTN) {
             if (warp >= 2) attention_phase(p, pos, grp, trace != nullptr ? trace + 1 + 2 * n_phases : nullptr);
         } else {
-            glue_phase(p, warp, lane);
+            glue_phase(p, warp, lane, reinterpret_cast<float*>(smem + WORK_BYTES + GLUE_RED_OFS));
         }
         if (threadIdx.x < 3 && ph + 1 < n_phases && phases[ph + 1].type == CHAIN_GEMM) {
             // the TMA unit fetches a descriptor from global memory on first use: start that before the barrier
