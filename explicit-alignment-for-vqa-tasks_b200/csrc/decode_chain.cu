@@ -205,31 +205,32 @@ __device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// 1-D bulk copy global -> shared (TMA engine, no tensor map): one instruction per contiguous history instead of one LDGSTS per
-// 512 bytes (measured: the 144 cp.async warp-instructions of an item kept the LSU busy for ~2800 cycles per item)
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
+constexpr int KV_BOX = 16;                // cache rows per TMA box (2 KB); staged histories are padded to a multiple of it
 
-// staging layout of one item: K rows [n][64] bf16 | V rows [n][64] bf16 | scores [n] fp32 | key validity [n] int32
+// staging layout of one item (1024-byte aligned: the rows are written by TMA with SWIZZLE_128B, i.e. the 16-byte chunk c of
+// row t sits at chunk c ^ (t & 7)):  K rows [nr][64] bf16 | V rows [nr][64] bf16 | scores [n] fp32 | key validity [n] int32
+__device__ __forceinline__ int att_rows(int n) { return (n + KV_BOX - 1) / KV_BOX * KV_BOX; }
+__device__ __forceinline__ int att_hist_bytes(int n) { return (2 * att_rows(n) * HD * 2 + n * 8 + 1023) & ~1023; }
+
+// The head's K / V history [0, pos) by TMA boxes of 16 rows through the per-layer tensor map of the cache (one thread, ~2 x 9
+// instructions per item; the first version issued 144 LDGSTS warp-instructions per item and kept the LSU busy for ~2800 cycles),
+// swizzled so that a LANE can later read a whole key row without bank conflicts.  The validity words travel by cp.async.
 __device__ __forceinline__ void att_issue_loads(const ChainPhase& p, int item, int pos, uint8_t* buf, int gtid, uint32_t bar) {
-    const int b = item / p.H, h = item - b * p.H;
-    const bf16* kbase = p.cache + (static_cast<int64_t>(b) * p.H + h) * p.Tmax * HD;
-    const bf16* vbase = kbase + static_cast<int64_t>(p.B) * p.H * p.Tmax * HD;
-    const int n = pos + 1;
-    bf16* Ks = reinterpret_cast<bf16*>(buf);
-    bf16* Vs = Ks + static_cast<size_t>(n) * HD;
-    int* vm = reinterpret_cast<int*>(Vs + static_cast<size_t>(n) * HD) + n;
+    const int b = item / p.H;
+    const int n = pos + 1, nr = att_rows(n);
     if (gtid == 0 && pos > 0) {
         // the buffer was last READ through the generic proxy (the item two back): order those reads before the async writes
         ptx::fence_proxy_async_smem();
-        const uint32_t bytes = static_cast<uint32_t>(pos) * HD * 2;
-        ptx::mbar_arrive_expect_tx(bar, 2 * bytes);
-        bulk_copy_g2s(ptx::smem_u32(Ks), kbase, bytes, bar);
-        bulk_copy_g2s(ptx::smem_u32(Vs), vbase, bytes, bar);
+        const int nbox = (pos + KV_BOX - 1) / KV_BOX;
+        const int row_k = item * p.Tmax, row_v = row_k + p.B * p.H * p.Tmax;
+        const uint32_t ks = ptx::smem_u32(buf), vs = ks + static_cast<uint32_t>(nr) * HD * 2;
+        ptx::mbar_arrive_expect_tx(bar, static_cast<uint32_t>(2 * nbox * KV_BOX * HD * 2));
+        for (int i = 0; i < nbox; ++i) {
+            ptx::tma_load_2d(ks + i * KV_BOX * HD * 2, &p.map_a, bar, 0, row_k + i * KV_BOX);
+            ptx::tma_load_2d(vs + i * KV_BOX * HD * 2, &p.map_a, bar, 0, row_v + i * KV_BOX);
+        }
     }
-    // (a global load of the validity word inside the score loop costs an L2 round trip per four keys)
+    int* vm = reinterpret_cast<int*>(buf + 2 * nr * HD * 2) + n;
     const int* vrow = p.valid + static_cast<int64_t>(b) * p.valid_stride;
     for (int t = gtid; t < n; t += 128) cp_async_4(ptx::smem_u32(vm + t), vrow + t);
     cp_async_commit();
@@ -256,13 +257,9 @@ __device__ __forceinline__ QkvRaw att_load_qkv(const ChainPhase& p, int item, in
     return r;
 }
 
-#define ATT_T(i) do { if (dbg != nullptr) { const long long now_ = clock64(); seg[i] += now_ - tprev; tprev = now_; } } while (0)
-__device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, AttGroup& g, unsigned long long* dbg_in) {
-    unsigned long long* dbg = (blockIdx.x == 0 && g.gid == 0 && g.gtid == 0) ? dbg_in : nullptr;
-    long long seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tprev = clock64();
-    const int n = pos + 1;
-    const int hist_bytes = (2 * n * HD * 2 + n * 8 + 127) & ~127;  // K, V rows + scores + validity (16-byte aligned rows)
+__device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, AttGroup& g) {
+    const int n = pos + 1, nr = att_rows(n);
+    const int hist_bytes = att_hist_bytes(n);
     const bool dbl = 2 * hist_bytes + ATT_FIXED <= ATT_GROUP_BYTES;
     uint8_t* bufs[2] = {g.base, g.base + hist_bytes};
     float* fixed = reinterpret_cast<float*>(g.base + (dbl ? 2 : 1) * hist_bytes);
@@ -283,108 +280,98 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, At
     }
     int k = 0;
     for (int item = first; item < n_items; item += stride, ++k) {
-        uint8_t* buf = bufs[dbl ? (k & 1) : 0];
+        const int bi = dbl ? (k & 1) : 0;
+        uint8_t* buf = bufs[bi];
         const int next = item + stride;
         const bool prefetch = dbl && next < n_items;
-        if (prefetch) att_issue_loads(p, next, pos, bufs[(k + 1) & 1], g.gtid, g.bar[(k + 1) & 1]);
+        if (prefetch) att_issue_loads(p, next, pos, bufs[bi ^ 1], g.gtid, g.bar[bi ^ 1]);
         QkvRaw nxt = {0.f, 0.f, 0.f, 0.f};
         if (next < n_items) nxt = att_load_qkv(p, next, g.gtid);              // latency hidden behind this item's reduction
-        ATT_T(0);
         const float a0 = cur.a0 + cur.b0, a1 = cur.a1 + cur.b1;
         const int b = item / p.H, h = item - b * p.H;
-        bf16* Ks = reinterpret_cast<bf16*>(buf);
-        bf16* Vs = Ks + static_cast<size_t>(n) * HD;
-        float* sc = reinterpret_cast<float*>(Vs + static_cast<size_t>(n) * HD);
+        uint8_t* Ks = buf;
+        uint8_t* Vs = buf + nr * HD * 2;
+        float* sc = reinterpret_cast<float*>(Vs + nr * HD * 2);
         const int* vm = reinterpret_cast<const int*>(sc + n);
-        bf16* kbase = p.cache + (static_cast<int64_t>(b) * p.H + h) * p.Tmax * HD;
+        bf16* kbase = p.cache + static_cast<int64_t>(item) * p.Tmax * HD;
         bf16* vhead = kbase + static_cast<int64_t>(p.B) * p.H * p.Tmax * HD;
-        if (g.gtid < HD) {
-            sq[g.gtid] = a0 * 0.125f;                                              // head_dim ** -0.5 folded into q
-            const bf16 kv = __float2bfloat16(a1);
-            kbase[static_cast<int64_t>(pos) * HD + g.gtid] = kv;
-            Ks[pos * HD + g.gtid] = kv;
-            if (p.zero != nullptr) p.zero[static_cast<int64_t>(b) * d + h * HD + g.gtid] = 0.f;
-        } else {
-            const bf16 vv = __float2bfloat16(a0);
-            vhead[static_cast<int64_t>(pos) * HD + g.gtid - HD] = vv;
-            Vs[pos * HD + g.gtid - HD] = vv;
-        }
-        if (prefetch) cp_async_wait_group<1>();        // (the validity words still travel by cp.async)
+        if (prefetch) cp_async_wait_group<1>();        // (the validity words travel by cp.async)
         else cp_async_wait_group<0>();
         if (pos > 0) {
-            const int bi = dbl ? (k & 1) : 0;
-            ptx::mbar_wait(g.bar[bi], g.parity[bi]);
-            g.parity[bi] ^= 1;
+            ptx::mbar_wait(g.bar[bi], g.parity[bi]);   // history boxes have landed (the last one may cover row `pos` with stale
+            g.parity[bi] ^= 1;                         // bytes: the new row is written only now)
         }
-        ATT_T(1);
-        named_bar_sync(bar_id, 128);
-        ATT_T(2);
-        const int ks = lane >> 3, cg = lane & 7;
-        float q8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) q8[i] = sq[cg * 8 + i];
-        const int chunk = (n + 3) >> 2;
-        const int t0 = warp * chunk, t1 = min(n, t0 + chunk);
-#pragma unroll 3
-        for (int tb = t0; tb < t1; tb += 4) {
-            const int t = tb + ks;
-            const bool ok = t < t1;
-            float acc = 0.f;
-            if (ok) {
-                const uint4 u = *reinterpret_cast<const uint4*>(Ks + t * HD + cg * 8);
-                float2 f;
-                f = unpack_bf16x2(u.x); acc = q8[0] * f.x + q8[1] * f.y;
-                f = unpack_bf16x2(u.y); acc += q8[2] * f.x + q8[3] * f.y;
-                f = unpack_bf16x2(u.z); acc += q8[4] * f.x + q8[5] * f.y;
-                f = unpack_bf16x2(u.w); acc += q8[6] * f.x + q8[7] * f.y;
+        // this step's q / k / v: k, v go to the cache and to row `pos` of the staged history (swizzled like the TMA rows)
+        {
+            const int e = g.gtid & 63, sw = ((e >> 3) ^ (pos & 7)) << 4;
+            if (g.gtid < HD) {
+                sq[e] = a0 * 0.125f;                                               // head_dim ** -0.5 folded into q
+                const bf16 kv = __float2bfloat16(a1);
+                kbase[static_cast<int64_t>(pos) * HD + e] = kv;
+                *reinterpret_cast<bf16*>(Ks + pos * 128 + sw + (e & 7) * 2) = kv;
+                if (p.zero != nullptr) p.zero[static_cast<int64_t>(b) * d + h * HD + e] = 0.f;
+            } else {
+                const bf16 vv = __float2bfloat16(a0);
+                vhead[static_cast<int64_t>(pos) * HD + e] = vv;
+                *reinterpret_cast<bf16*>(Vs + pos * 128 + sw + (e & 7) * 2) = vv;
             }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            if (ok && cg == 0) sc[t] = vm[t] ? acc : -INFINITY;
         }
-        __syncwarp();
-        ATT_T(3);
+        named_bar_sync(bar_id, 128);
+        // scores: one KEY per lane (no shuffles): warp w takes the 32-key blocks w, w + 4, ...
+        float q[64];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float4 f = *reinterpret_cast<const float4*>(sq + 4 * c);
+            q[4 * c] = f.x; q[4 * c + 1] = f.y; q[4 * c + 2] = f.z; q[4 * c + 3] = f.w;
+        }
         float mx = -INFINITY;
-        for (int t = t0 + lane; t < t1; t += 32) mx = fmaxf(mx, sc[t]);
+        for (int t = warp * 32 + lane; t < n; t += 128) {
+            const uint8_t* row = Ks + t * 128;
+            const int x = t & 7;
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 u = *reinterpret_cast<const uint4*>(row + ((c ^ x) << 4));
+                float2 f;
+                f = unpack_bf16x2(u.x); acc0 += q[8 * c] * f.x; acc1 += q[8 * c + 1] * f.y;
+                f = unpack_bf16x2(u.y); acc0 += q[8 * c + 2] * f.x; acc1 += q[8 * c + 3] * f.y;
+                f = unpack_bf16x2(u.z); acc0 += q[8 * c + 4] * f.x; acc1 += q[8 * c + 5] * f.y;
+                f = unpack_bf16x2(u.w); acc0 += q[8 * c + 6] * f.x; acc1 += q[8 * c + 7] * f.y;
+            }
+            const float sv = vm[t] ? acc0 + acc1 : -INFINITY;
+            sc[t] = sv;
+            mx = fmaxf(mx, sv);
+        }
         mx = warp_max(mx);
         const float muse = (mx == -INFINITY) ? 0.f : mx;
         float sum = 0.f;
-        for (int t = t0 + lane; t < t1; t += 32) {
+        for (int t = warp * 32 + lane; t < n; t += 128) {
             const float pr = __expf(sc[t] - muse);
             sc[t] = pr;
             sum += pr;
         }
         sum = warp_sum(sum);
         __syncwarp();
-        ATT_T(4);
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 3
-        for (int t = t0 + ks; t < t1; t += 4) {
-            const float pr = sc[t];
-            const uint4 u = *reinterpret_cast<const uint4*>(Vs + t * HD + cg * 8);
-            float2 f;
-            f = unpack_bf16x2(u.x); acc[0] += pr * f.x; acc[1] += pr * f.y;
-            f = unpack_bf16x2(u.y); acc[2] += pr * f.x; acc[3] += pr * f.y;
-            f = unpack_bf16x2(u.z); acc[4] += pr * f.x; acc[5] += pr * f.y;
-            f = unpack_bf16x2(u.w); acc[6] += pr * f.x; acc[7] += pr * f.y;
+        // P.V: lane owns output dimensions 2 lane, 2 lane + 1; one broadcast probability + one conflict-free row read per key
+        float o0 = 0.f, o1 = 0.f;
+        const int vchunk = lane >> 2, vofs = (lane & 3) * 4;
+        for (int t0 = warp * 32; t0 < n; t0 += 128) {
+            const int cnt = min(32, n - t0);
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                const int t = t0 + j;
+                const float pr = sc[t];
+                const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(Vs + t * 128 + ((vchunk ^ (t & 7)) << 4) + vofs));
+                o0 += pr * f.x;
+                o1 += pr * f.y;
+            }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-        }
-        if (ks == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) part[warp * 64 + cg * 8 + i] = acc[i];
-        }
+        part[warp * 64 + 2 * lane] = o0;
+        part[warp * 64 + 2 * lane + 1] = o1;
         if (lane == 0) {
             part_m[warp] = mx;
             part_l[warp] = sum;
         }
-        ATT_T(5);
         named_bar_sync(bar_id, 128);
         if (g.gtid < HD) {
             const float m = fmaxf(fmaxf(part_m[0], part_m[1]), fmaxf(part_m[2], part_m[3]));
@@ -402,11 +389,6 @@ __device__ __forceinline__ void attention_phase(const ChainPhase& p, int pos, At
         named_bar_sync(bar_id, 128);           // sq / part / this buffer are rewritten by the next item
         if (!dbl && next < n_items) att_issue_loads(p, next, pos, bufs[0], g.gtid, g.bar[0]);
         cur = nxt;
-        ATT_T(6);
-    }
-    if (dbg != nullptr) {
-        for (int i = 0; i < 7; ++i) dbg[i] = static_cast<unsigned long long>(seg[i]);
-        dbg[7] = static_cast<unsigned long long>(k);
     }
 }
 
@@ -557,7 +539,7 @@ decode_chain_kernel(const ChainPhase* __restrict__ phases, int n_phases, int pos
                 gemm_epilogue(p, accs, tfull_bar, tempty_bar, tmem_base, smem_epi + (warp - 2) * EPI_BUF, warp, lane);
             }
         } else if (p.type == CHAIN_ATTN) {
-            if (warp >= 2) attention_phase(p, pos, grp, trace != nullptr ? trace + 1 + 2 * n_phases : nullptr);
+            if (warp >= 2) attention_phase(p, pos, grp);
         } else {
             glue_phase(p, warp, lane, reinterpret_cast<float*>(smem + WORK_BYTES + GLUE_RED_OFS));
         }
@@ -586,7 +568,8 @@ static_assert(sizeof(ChainPhase) % 128 == 0, "tensor maps inside an array of pha
 
 bool decode_chain_supported(int max_keys) {
     // the attention phases stage one head's whole K / V history per four-warp group
-    return ((2 * max_keys * dc::HD * 2 + max_keys * 8 + 127) & ~127) + dc::ATT_FIXED <= dc::ATT_GROUP_BYTES;
+    const int nr = (max_keys + dc::KV_BOX - 1) / dc::KV_BOX * dc::KV_BOX;
+    return ((2 * nr * dc::HD * 2 + max_keys * 8 + 1023) & ~1023) + dc::ATT_FIXED <= dc::ATT_GROUP_BYTES;
 }
 
 void chain_gemm_phase(ChainPhase& p, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, int split, int mode, void* out,
@@ -612,6 +595,8 @@ void chain_attn_phase(ChainPhase& p, const float* qkv_acc, const float* qkv_bias
     p.type = CHAIN_ATTN;
     p.qkv_acc = qkv_acc; p.bias = qkv_bias; p.cache = cache; p.valid = valid; p.valid_stride = valid_stride; p.o = o; p.zero = zero;
     p.B = B; p.H = H; p.Tmax = Tmax;
+    // the layer's cache as a [2 * B * H * Tmax, 64] bf16 matrix (K block, then V block), boxes of 16 rows, SWIZZLE_128B
+    p.map_a = gemm_make_map(cache, 2 * B * H * Tmax, dc::HD, dc::HD, dc::KV_BOX, MAP_OPERAND);
 }
 
 void chain_glue_phase(ChainPhase& p, float* x, const float* acc, const float* bias, const float* gamma, const float* beta, bf16* u, int rows,

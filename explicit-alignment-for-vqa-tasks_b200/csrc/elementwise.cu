@@ -209,17 +209,30 @@ __global__ void __launch_bounds__(128) decode_residual_ln_kernel(float* __restri
     __shared__ float red[4];
     const int row = blockIdx.x, n4 = d >> 2;
     float4* xp = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * d);
-    float4 v[4];
-    float sum = 0.f;
+    // every global load of the row (x, accumulator, bias, gamma, beta) is issued before the first dependent store: issue is
+    // in order, so a store between two loads serialises their L2 round trips (measured in the persistent decode kernel:
+    // 8 dependent trips cost 4 us; this kernel is pure latency)
+    float4 v[4], a[4], bb[4], g[4], be[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int c = threadIdx.x + 128 * i;
         if (c < n4) {
             v[i] = xp[c];
             if (acc != nullptr) {
-                const float4 a = reinterpret_cast<const float4*>(acc + static_cast<size_t>(row) * d)[c];
-                const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c);
-                v[i].x += a.x + b.x; v[i].y += a.y + b.y; v[i].z += a.z + b.z; v[i].w += a.w + b.w;
+                a[i] = reinterpret_cast<const float4*>(acc + static_cast<size_t>(row) * d)[c];
+                bb[i] = __ldg(reinterpret_cast<const float4*>(bias) + c);
+            }
+            g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+            be[i] = __ldg(reinterpret_cast<const float4*>(beta) + c);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + 128 * i;
+        if (c < n4) {
+            if (acc != nullptr) {
+                v[i].x += a[i].x + bb[i].x; v[i].y += a[i].y + bb[i].y; v[i].z += a[i].z + bb[i].z; v[i].w += a[i].w + bb[i].w;
                 xp[c] = v[i];
             }
             sum += v[i].x + v[i].y + v[i].z + v[i].w;
@@ -231,8 +244,8 @@ __global__ void __launch_bounds__(128) decode_residual_ln_kernel(float* __restri
     for (int i = 0; i < 4; ++i) {
         const int c = threadIdx.x + 128 * i;
         if (c < n4) {
-            const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
-            sq += a * a + b * b + e * e + f * f;
+            const float e0 = v[i].x - mean, e1 = v[i].y - mean, e2 = v[i].z - mean, e3 = v[i].w - mean;
+            sq += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
         }
     }
     const float rstd = rsqrtf(block_sum_128(sq, red) / d + eps);
@@ -241,10 +254,9 @@ __global__ void __launch_bounds__(128) decode_residual_ln_kernel(float* __restri
     for (int i = 0; i < 4; ++i) {
         const int c = threadIdx.x + 128 * i;
         if (c < n4) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c), b = __ldg(reinterpret_cast<const float4*>(beta) + c);
             uint2 o;
-            o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-            o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+            o.x = pack_bf16x2((v[i].x - mean) * rstd * g[i].x + be[i].x, (v[i].y - mean) * rstd * g[i].y + be[i].y);
+            o.y = pack_bf16x2((v[i].z - mean) * rstd * g[i].z + be[i].z, (v[i].w - mean) * rstd * g[i].w + be[i].w);
             up[c] = o;
         }
     }

@@ -923,12 +923,6 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
             cnt[ph[i].type]++;
             if (ph[i].type == CHAIN_GEMM) by_shape[(i - 1) % 7] += static_cast<double>(all - begin) * 1e-3;
         }
-        {
-            const unsigned long long* a = t.data() + 1 + 2 * n_chain;
-            fprintf(stderr, "[eavqa] attention phase, last layer, group 0 of CTA 0, %llu items, cycles per item: issue next %llu, write q/k/v + wait loads %llu, "
-                            "barrier %llu, scores %llu, softmax %llu, PV %llu, merge + 2 barriers %llu\n", a[7], a[0] / a[7], a[1] / a[7], a[2] / a[7],
-                    a[3] / a[7], a[4] / a[7], a[5] / a[7], a[6] / a[7]);
-        }
         fprintf(stderr, "[eavqa] decode chain, last step: %.1f us total; per phase (CTA 0 work + wait at barrier, us): gemm %.2f + %.2f (x%d), "
                         "attention %.2f + %.2f (x%d), glue %.2f + %.2f (x%d); gemm phases per layer: qkv %.2f o %.2f fc %.2f pr %.2f\n",
                 static_cast<double>(t[2 * n_chain] - t[0]) * 1e-3, work[0] / cnt[0], wait[0] / cnt[0], cnt[0], work[1] / cnt[1], wait[1] / cnt[1],
