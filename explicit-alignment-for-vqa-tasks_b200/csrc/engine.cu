@@ -743,10 +743,14 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     int* part_idx = nullptr;
     unsigned* arrivals = nullptr;
     const size_t kv_layer = static_cast<size_t>(B) * Tmax * 2 * d;
-    // single-token steps: one persistent cooperative kernel per step (decode_chain.cu) instead of ~7 launches per layer
-    // (EAVQA_DECODE_CHAIN=0, read per call, selects the launch-per-operation path below: A/B measurements and tests)
+    // single-token steps as ONE persistent cooperative kernel per step (decode_chain.cu) instead of ~7 launches per layer.
+    // Opt-in (EAVQA_DECODE_CHAIN=1, read per call): measured on B200 (profiles/README.md, round 2) the persistent kernel does
+    // NOT beat the launch-per-operation path below -- 28.9 vs 25.3 ms per 128-answer batch -- because a decode step is a chain
+    // of dependent memory round trips (TMA load -> MMA -> reduce-add completion -> barrier: 6-10 us per projection whether the
+    // boundary is a grid barrier or a kernel launch), and its attention phases keep fewer bytes in flight than five resident
+    // CTAs per SM do.  It stays parity-tested as the starting point for overlapping two half-batches.
     const char* chain_opt = getenv("EAVQA_DECODE_CHAIN");
-    const bool chain_env = !(chain_opt != nullptr && chain_opt[0] == '0');
+    const bool chain_env = chain_opt != nullptr && chain_opt[0] == '1';
     const bool use_chain = chain_env && max_new > 1 && B <= 128 && d % 64 == 0 && decode_chain_supported(Tmax);
     const int n_chain = 1 + 7 * L;
     ChainPhase* chain_dev = nullptr;
