@@ -105,6 +105,11 @@ class _TrainStepFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         grads, model = ctx.grads, ctx.model
+        if getattr(ctx, "consumed", False):
+            # the flat gradient buffer was handed over by the first backward (and possibly rescaled in place since)
+            raise RuntimeError("ClipCaptionPrefixB200: backward through the same step a second time; run forward again "
+                               "(the reference would raise 'Trying to backward through the graph a second time' too)")
+        ctx.consumed = True
         ctx.grads = None
         if grads is None:
             return (None,) * (6 + len(model._param_list))

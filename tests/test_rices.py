@@ -140,3 +140,28 @@ def test_rices_rerank_matches_oracle():
         sure = (np.concatenate(([np.inf], s[:-1] - s[1:])) > 1e-5) & (np.concatenate((s[:-1] - s[1:], [np.inf])) > 1e-5)
         assert (pos[m, :n][sure] == pr[m, :n][sure]).all()
         assert sorted(pos[m, :n].tolist()) == sorted(pr[m, :n].tolist())
+
+
+# ------------------------------------------------------------------------------------------------ faiss fixture (when someone made it)
+def test_oracle_and_kernel_against_faiss_fixture():
+    """``oracle/pin_rices_with_faiss.py`` records faiss' own scores / indices where faiss is installable (it is not in
+    this image).  When that fixture exists the oracle -- and, on a B200, the kernel -- are checked against it; until
+    then the RICES oracle stays 'parity unpinned' and this test says so by skipping."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "rices_faiss.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/rices_faiss.json absent: faiss cannot be installed in this image (oracle/pin_rices_with_faiss.py)")
+    from oracle import pin_rices_with_faiss as pin
+    with open(path) as f:
+        fx = json.load(f)
+    for c in fx["cases"]:
+        q, db = pin.make(c["name"], c["M"], c["N"], c["D"], c["seed"])
+        D, I = orc.knn_inner_product(q, db, c["k"])
+        Df, If = np.array(c["scores"]), np.array(c["index"])
+        ok = If >= 0
+        assert np.array_equal(ok, I >= 0) and np.abs(D[ok] - Df[ok]).max() < 2e-6
+        if torch.cuda.is_available():
+            from eavqa_b200.rices import knn_inner_product
+            Dg, Ig = knn_inner_product(torch.from_numpy(q).cuda(), torch.from_numpy(db).cuda(), c["k"])
+            assert np.abs(Dg.cpu().numpy()[ok] - Df[ok]).max() < TOL

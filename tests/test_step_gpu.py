@@ -166,6 +166,45 @@ def test_step_is_deterministic_and_scales_with_upstream_gradient():
     assert torch.allclose(g3, 2 * g1, rtol=1e-4, atol=1e-6 * float(g1.abs().max()))
 
 
+def test_flat_adamw_follows_schedulers_and_accumulates_micro_batches():
+    """``FlatAdamW`` against ``torch.optim.AdamW`` on the same model through two optimiser steps of two micro-batches each
+    (Lightning ``accumulate_grad_batches=2``, README.md:199-206) under a warm-up scheduler that drives ``param_groups`` --
+    the executor's ``get_constant_schedule_with_warmup`` does exactly that (clipcap_exector.py:101-109).  Also: a second
+    backward through one step raises, as autograd does for the reference."""
+    from eavqa_b200.optim import FlatAdamW
+    case = CASES["train_tiny_transformer"]
+    lm_w, mapper_w, batch, cfg = build_case(case)
+    halves = [{k: v[:2] for k, v in batch.items()}, {k: v[2:] for k, v in batch.items()}]
+
+    def fwd(model, b):
+        return model(question_tokens=b["input_ids"], labels=b["labels"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"]).loss
+
+    ref = build_model(case, lm_w, mapper_w)
+    opt_r = torch.optim.AdamW(ref.parameters(), lr=1e-3)
+    sch_r = torch.optim.lr_scheduler.LambdaLR(opt_r, lambda s: min(1.0, (s + 1) / 2))
+    mine = build_model(case, lm_w, mapper_w)
+    fwd(mine, halves[0])            # builds the engine / flat buffer
+    opt_m = FlatAdamW(mine, lr=1e-3)
+    sch_m = torch.optim.lr_scheduler.LambdaLR(opt_m, lambda s: min(1.0, (s + 1) / 2))
+    for _ in range(2):
+        opt_r.zero_grad(set_to_none=True)
+        opt_m.zero_grad()
+        for b in halves:
+            (fwd(ref, b) / 2).backward()
+            (fwd(mine, b) / 2).backward()
+            opt_m.accumulate()
+        opt_r.step(); sch_r.step()
+        opt_m.step(); sch_m.step()
+        assert opt_m.param_groups[0]["lr"] == pytest.approx(opt_r.param_groups[0]["lr"])
+    a = torch.cat([p.detach().flatten() for p in ref.parameters()])
+    b_ = torch.cat([p.detach().flatten() for p in mine.parameters()])
+    assert float((a - b_).abs().max()) <= 2e-5 + 1e-3 * 1e-3          # lr-sized updates; identical up to fp32 reduction order
+    loss = fwd(mine, halves[0])
+    loss.backward()
+    with pytest.raises(RuntimeError):
+        loss.backward()
+
+
 def test_all_labels_ignored_gives_nan_loss_like_the_reference():
     case = CASES["train_tiny_mlp"]
     lm_w, mapper_w, batch, cfg = build_case(case)
