@@ -43,6 +43,7 @@ WORKLOAD_TEXT = {
           "(T=50), synthetic CLIP ViT-L/14 768-d embeddings, 64 samples per GPU (512 on 8 GPUs)",
 }
 WORKLOAD = "c2"
+ALLREDUCE_NOTE = "none (one GPU)"
 
 
 def peaks():
@@ -183,6 +184,7 @@ def run_reference(args, rank):
 def workload_config(world, note=""):
     W = C5 if WORKLOAD == "c5" else C2
     return {"workload": WORKLOAD_TEXT[WORKLOAD], "batch_per_gpu": W["batch_per_gpu"], "global_batch": W["batch_per_gpu"] * world,
+            "allreduce": ALLREDUCE_NOTE,
             "parallelism": "dp%d" % world, "optimizer": "fused AdamW on the mapper (in the timed region)",
             "l2": "inputs larger than L2: ~3 GB of activations per step >> 126 MB L2, no flush needed", "note": note}
 
@@ -203,6 +205,7 @@ def main():
     ap.add_argument("--only-timed", action="store_true", help="run only warm-up + the timed region (for ncu launch lists)")
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="N > 1: bucketed gradient all-reduce overlapped with the mapper backward instead of one all-reduce after the step")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: cap on NCCL's CTAs per collective (0 = NCCL's default)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the headline): 256 samples per GPU; strong: 256 samples in total, 256 / N per GPU (SURVEY.md 8d)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
@@ -228,7 +231,14 @@ def main():
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            pg_options = None
+            if args.nccl_max_ctas > 0:
+                # cap the SMs NCCL's kernels may take, so that a collective overlapped with the step's own kernels does not
+                # starve them (round 1: with the default channel count the bucketed overlap LOST at N = 8)
+                pg_options = dist.ProcessGroupNCCL.Options()
+                pg_options.config.max_ctas = args.nccl_max_ctas
+                pg_options.config.min_ctas = min(args.nccl_max_ctas, 4)
+            dist.init_process_group("nccl", device_id=dev, pg_options=pg_options)
             dist.all_reduce(torch.zeros(1, device=dev))
             torch.cuda.synchronize()
         finally:
@@ -267,6 +277,11 @@ def main():
     # step, N = 8 11.50 vs 11.26 ms/step (NVLS makes the 167 MB all-reduce cost only ~0.4 ms; NCCL's CTAs slow the GEMMs they
     # overlap by about as much).  Default: one all-reduce of the whole flat buffer after the step.
     reducer = OverlappedGradReducer(model) if (world > 1 and args.overlap_allreduce) else None
+    global ALLREDUCE_NOTE
+    if world > 1:
+        ALLREDUCE_NOTE = ("bucketed NCCL all-reduce overlapped with the mapper backward" if reducer is not None else
+                          "one NCCL all-reduce of the flat fp32 mapper gradient after the step") + \
+                         (", NCCL capped at %d CTAs" % args.nccl_max_ctas if args.nccl_max_ctas > 0 else "")
 
     def step(b):
         out = model(question_tokens=b["input_ids"], labels=b["labels"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"])

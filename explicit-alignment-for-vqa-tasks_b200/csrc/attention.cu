@@ -238,6 +238,131 @@ __global__ void __launch_bounds__(128, 4) lm_attention_fwd_kernel(const bf16* __
     }
 }
 
+// Sequences of at most one block (T <= 64: the training step, T = 50): PERSISTENT CTAs walk the (sample, head) items with
+// the next item's q / k / v tiles and validity words already streaming into a second buffer set while the current item is
+// reduced, and O leaves through shared memory as 16-byte coalesced stores.  Round-2 reason: the one-CTA-per-item kernel above
+// loads, then computes, then stores -- every CTA of a wave in lock-step, so DRAM idles during the math (2.7 TB/s of 6.5).
+constexpr int kFwdTile = BLK * LDS;                                 // bf16 elements of one staged tile
+constexpr int kFwdSetBytes = 3 * kFwdTile * 2 + BLK * 4;            // q, k, v tiles + validity words
+__global__ void __launch_bounds__(128, 4) lm_attention_fwd_single_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
+                                                                      bf16* __restrict__ o, float* __restrict__ lse, int T,
+                                                                      int H, int n_items) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ __align__(16) uint8_t fwd_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int d = H * HD;
+    const int64_t ld = 3 * d;
+    const float scale = 0.125f;     // head_dim ** -0.5  (HF modeling_gpt2.py:96-98)
+
+    auto issue = [&](int item, int set) {
+        const int b = item / H, h = item - b * H;
+        bf16* Qs = reinterpret_cast<bf16*>(fwd_smem + set * kFwdSetBytes);
+        int* kv = reinterpret_cast<int*>(Qs + 3 * kFwdTile);
+        const bf16* base = qkv + static_cast<int64_t>(b) * T * ld + h * HD;
+        load_tile_async(Qs, base, ld, 0, T, tid);
+        load_tile_async(Qs + kFwdTile, base + d, ld, 0, T, tid);
+        load_tile_async(Qs + 2 * kFwdTile, base + 2 * d, ld, 0, T, tid);
+        if (tid < BLK) {
+            if (tid < T) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(kv + tid)), "l"(valid + b * T + tid) : "memory");
+            else kv[tid] = 0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int item = blockIdx.x;
+    if (item < n_items) issue(item, 0);
+    for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+        const int set = it & 1;
+        cp_async_wait_all();
+        __syncthreads();                          // this item's tiles are visible; every warp is done with the other set
+        if (item + static_cast<int>(gridDim.x) < n_items) issue(item + gridDim.x, set ^ 1);
+        bf16* Qs = reinterpret_cast<bf16*>(fwd_smem + set * kFwdSetBytes);
+        const bf16* Ks = Qs + kFwdTile;
+        const bf16* Vs = Qs + 2 * kFwdTile;
+        const int* kvalid = reinterpret_cast<const int*>(Qs + 3 * kFwdTile);
+        const int b = item / H, h = item - b * H;
+
+        uint32_t qf[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) load_a(qf[ks], Qs, warp * 16, ks * 16, lane);
+        float sacc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sacc[i][e] = 0.f;
+        warp_gemm_nt(sacc, qf, Ks, lane);
+        float rmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = nt * 8 + 2 * t4 + (e & 1);
+                const int row = warp * 16 + g + ((e >> 1) << 3);
+                const bool ok = kvalid[col] && (col <= row);
+                const float sv = ok ? sacc[nt][e] * scale : -INFINITY;
+                sacc[nt][e] = sv;
+                rmax[e >> 1] = fmaxf(rmax[e >> 1], sv);
+            }
+        float muse[2], l_i[2] = {0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 1));
+            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 2));
+            muse[r] = (rmax[r] == -INFINITY) ? 0.f : rmax[r];
+        }
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float p0 = __expf(sacc[nt][0] - muse[0]), p1 = __expf(sacc[nt][1] - muse[0]);
+            const float p2 = __expf(sacc[nt][2] - muse[1]), p3 = __expf(sacc[nt][3] - muse[1]);
+            l_i[0] += p0 + p1;
+            l_i[1] += p2 + p3;
+            pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+        float oacc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oacc[i][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t bfr[4];
+                load_b_trans(bfr, Vs, np * 16, ks * 16, lane);
+                mma_bf16(oacc[2 * np], pf[ks], bfr[0], bfr[1]);
+                mma_bf16(oacc[2 * np + 1], pf[ks], bfr[2], bfr[3]);
+            }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
+            l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
+        }
+        // O through this warp's own 16 rows of the q tile (only this warp ever reads them), then 16-byte row-contiguous stores
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = warp * 16 + g + r * 8;
+            const float inv = l_i[r] > 0.f ? 1.0f / l_i[r] : 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+                *reinterpret_cast<uint32_t*>(Qs + row * LDS + nt * 8 + 2 * t4) = pack_bf16x2(oacc[nt][2 * r] * inv, oacc[nt][2 * r + 1] * inv);
+            if (lse != nullptr && t4 == 0 && row < T)
+                lse[(static_cast<int64_t>(b) * H + h) * T + row] = (l_i[r] > 0.f) ? rmax[r] + logf(l_i[r]) : INFINITY;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = warp * 16 + (lane >> 3) + 4 * i, c = (lane & 7) * 8;
+            if (row < T)
+                *reinterpret_cast<uint4*>(o + (static_cast<int64_t>(b) * T + row) * d + h * HD + c) = *reinterpret_cast<const uint4*>(Qs + row * LDS + c);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ backward
 // One CTA per (batch, head); outer loop over key blocks j, inner over query blocks i >= j.
 __global__ void __launch_bounds__(128) lm_attention_bwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
@@ -521,15 +646,23 @@ __global__ void __launch_bounds__(128, 4) lm_attention_bwd_single_kernel(const b
     }
     __syncthreads();
     // one gradient at a time: acc(16 rows x 64) = A^T-or-A (from Ps / dSs) * B (from dOs / Qs / Ks)
+    // Gradients leave through the warp's own 16 rows of the V tile (nobody reads V after the dP product above) as 16-byte,
+    // row-contiguous stores: from the accumulator layout every store instruction would touch 8 rows with 16 bytes each.
     auto store_rows = [&](const float (&acc)[8][4], int col_off, float mul) {
+        __syncwarp();
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const int pos = warp * 16 + g + r * 8;
-            if (pos >= T) continue;
-            bf16* p = dbase + static_cast<int64_t>(pos) * ld + col_off;
+            const int row = warp * 16 + g + r * 8;
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt)
-                *reinterpret_cast<uint32_t*>(p + nt * 8 + 2 * t4) = pack_bf16x2(acc[nt][2 * r] * mul, acc[nt][2 * r + 1] * mul);
+                *reinterpret_cast<uint32_t*>(Vs + row * LDS + nt * 8 + 2 * t4) = pack_bf16x2(acc[nt][2 * r] * mul, acc[nt][2 * r + 1] * mul);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = warp * 16 + (lane >> 3) + 4 * i, c = (lane & 7) * 8;
+            if (row < T)
+                *reinterpret_cast<uint4*>(dbase + static_cast<int64_t>(row) * ld + col_off + c) = *reinterpret_cast<const uint4*>(Vs + row * LDS + c);
         }
     };
     {   // dV = P^T dO
@@ -1257,6 +1390,19 @@ __global__ void __launch_bounds__(128) mapper_attention_bwd_kernel(const bf16* _
 // ============================================================================================ launchers
 void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, int B, int T, int H, cudaStream_t s, bf16* kv_cache,
                       int Tmax) {
+    if (T <= BLK && kv_cache == nullptr) {
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(lm_attention_fwd_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFwdSetBytes));
+            configured = true;
+        }
+        const int n_items = B * H;
+        launch_kernel(lm_attention_fwd_single_kernel, dim3(std::min(n_items, 4 * num_sms())), dim3(128), 2 * kFwdSetBytes, s, qkv, valid, o,
+                      lse, T, H, n_items);
+        KERNEL_CHECK();
+        count_launch();
+        return;
+    }
     dim3 grid(ceil_div(T, BLK), H, B);
     if (kv_cache != nullptr) launch_kernel(lm_attention_fwd_kernel<true>, dim3(grid), dim3(128), 0, s, qkv, valid, o, lse, T, H, kv_cache, Tmax);
     else launch_kernel(lm_attention_fwd_kernel<false>, dim3(grid), dim3(128), 0, s, qkv, valid, o, lse, T, H, kv_cache, Tmax);
