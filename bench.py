@@ -375,13 +375,13 @@ def main():
     achieved = gemm_tf / (gemm_ms * 1e-3)
     step_tflops = GFLOP_PER_SAMPLE[WORKLOAD] * B / 1e3 / (ms_step * 1e-3)
     # DRAM traffic of the GEMM launches: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 196 GEMM launches
-    # of one step, per launch like `achieved` (profiles/r01_gemm_traffic_v24.json, made by tools/ncu_step_summary.py from
+    # of one step, per launch like `achieved` (profiles/r02_gemm_traffic_v1.json, made by tools/ncu_step_summary.py from
     # the committed launch list); algorithmic bytes per launch from the same per-launch records as the timings.
     import re
     alg = [float(m.group(2)) * int(m.group(1)) for m in re.finditer(r"launches=(\d+) .*alg_mbytes=([0-9.]+)", rep.value.decode())]
     alg_gb_per_launch = sum(alg) / 1e3 / max(nl.value, 1)
     traffic, traffic_note = None, "no ncu traffic summary under profiles/"
-    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic_v24.json")
+    tp = os.path.join(ROOT, "profiles", "r02_gemm_traffic_v1.json")
     if os.path.exists(tp) and WORKLOAD == "c2":
         with open(tp) as f:
             t = json.load(f)
@@ -458,11 +458,42 @@ def bench_generate(dev, eavqa_b200, syn, args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     T0 = host["input_ids"].shape[1] + 9 * (k + 1)
+
+    # prefill / decode split: the same call with max_length = 1 is the prefill (+ the first pick); the rest is the nine
+    # single-token steps.  Prefill is tensor-bound, a decode step HBM-bound: weights once + the KV history.
+    def gen1():
+        b = {kk: v.to(dev, non_blocking=True) for kk, v in host.items()}
+        return model.generate(question_tokens=b["input_ids"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"],
+                              max_length=1, pad_token_id=50256, eos_token_id=None)
+    for _ in range(2):
+        gen1()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        gen1()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_prefill = e0.elapsed_time(e1) / n
+    pk = peaks()
+    L_, d_, B_ = lm_cfg["n_layer"], lm_cfg["d_model"], c["batch"]
+    steps = c["max_length"] - 1
+    ms_step = (ms - ms_prefill) / steps
+    weight_bytes = L_ * 12 * d_ * d_ * 2 + ((lm_cfg["vocab"] + 63) // 64 * 64) * d_ * 2
+    kv_bytes = sum(B_ * (T0 + i) * L_ * 2 * d_ * 2 for i in range(1, steps + 1)) / steps          # mean history over the steps
+    step_gb = (weight_bytes + kv_bytes) / 1e9
+    prefill_tflops = 76.4 * B_ / 1e3 / (ms_prefill * 1e-3)
+    roofline = {"prefill": {"bound": "tensor", "ms": ms_prefill, "achieved": prefill_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
+                            "frac": prefill_tflops / pk["tflops"], "algorithmic_gflop_per_answer": 76.4},
+                "decode_step": {"bound": "hbm", "ms": ms_step, "steps": steps, "achieved": step_gb / (ms_step * 1e-3), "peak": pk["hbm"],
+                                "unit": "GB/s", "frac": step_gb / (ms_step * 1e-3) / pk["hbm"], "gbytes_per_step": step_gb,
+                                "weights_gb": weight_bytes / 1e9, "kv_history_gb": kv_bytes / 1e9,
+                                "note": "a decode step is ~170 dependent launches (7 per layer): split-K projection GEMMs, KV-cache "
+                                        "attention, residual + LayerNorm glue; bound by their latency chain, not by bytes (DESIGN.md)"}}
     return {"metric": "few_shot_vqa_answers_per_sec", "value": c["batch"] / (ms * 1e-3), "unit": "answers/s", "ms_per_batch": ms,
             "config": {"workload": "BASELINE configs[3]: 4-shot in-context prefixes, GPT-2 medium, batch 128, 10 new tokens, "
                                    "KV-cached greedy decode, host tensors in / token tensor out", "prompt_len": T0,
                        "tokens_out_shape": list(out.shape)},
-            "algorithmic_gflop_per_answer": 82.8, "tflops": 82.8 * c["batch"] / 1e3 / (ms * 1e-3)}
+            "algorithmic_gflop_per_answer": 82.8, "tflops": 82.8 * c["batch"] / 1e3 / (ms * 1e-3), "roofline": roofline}
 
 
 def bench_rices(with_cpu=True):

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -176,6 +177,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(f32x2 v) {
     float lo, hi;
     upk(v, lo, hi);
     return pack_bf16x2(lo, hi);
+}
+// fp16 pair (10 mantissa bits): the LM head's STORED logits.  They are read once more, by d logits = softmax - onehot, and a
+// trained GPT-2's logits sit at |z| ~ 30-150 where a bf16 ulp is 0.25-1.0 -- a 25 % error on every probability (round-2 test
+// at that scale: mapper-gradient cosine 0.9989); fp16 is 8x finer at the same 2 bytes and its range (65504) is ample.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(f32x2 v) {
+    float lo, hi;
+    upk(v, lo, hi);
+    return pack_f16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);

@@ -668,10 +668,10 @@ __global__ void __launch_bounds__(256) ce_dlogits_kernel(bf16* __restrict__ z, i
         const uint4 u = zp[c];
         float f[8];
         float2 t;
-        t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
-        t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
-        t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
-        t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+        t = unpack_f16x2(u.x); f[0] = t.x; f[1] = t.y;        // the head stores its logits as fp16; d logits go back as bf16,
+        t = unpack_f16x2(u.y); f[2] = t.x; f[3] = t.y;        // the dgrad GEMM's operand type, in place
+        t = unpack_f16x2(u.z); f[4] = t.x; f[5] = t.y;
+        t = unpack_f16x2(u.w); f[6] = t.x; f[7] = t.y;
         const int v0 = c * 8;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {

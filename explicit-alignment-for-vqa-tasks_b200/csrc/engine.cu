@@ -137,6 +137,13 @@ Engine::Engine(const eavqa_config& cfg) : cfg_(cfg) {
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     EAVQA_CHECK(major == 10, "eavqa_b200 needs an sm_100 (Blackwell B200) device; there is no fallback path");
+    {
+        // one device per process (one process per GPU, as under Lightning DDP / torchrun): kernel attributes, the RICES
+        // workspace, the zero-bias vector and the SM count are cached process-wide
+        static int first_device = -1;
+        if (first_device < 0) first_device = dev;
+        EAVQA_CHECK(first_device == dev, "eavqa_b200 is used on one CUDA device per process; this process already runs on another device");
+    }
     Vpad_ = static_cast<int>(round_up64(V_, 64));
     S_ = 0;
     auto add = [&](const std::string& name, int64_t rows, int64_t cols) {

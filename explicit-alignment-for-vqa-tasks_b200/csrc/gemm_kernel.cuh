@@ -44,7 +44,7 @@ enum EpiMode {
     EM_F32,                 // fp32 out (also split-K partials, added with TMA reduce)
     EM_F32_BIAS,            // fp32 out, + bias
     EM_F32_BIAS_RES,        // fp32 out = acc + bias + residual
-    EM_CE,                  // bf16 out + online-softmax statistics and the label's logit (LM head)
+    EM_CE,                  // fp16 (!) logits out + online-softmax statistics and the label's logit (LM head)
     EM_COUNT
 };
 
@@ -399,6 +399,12 @@ __device__ __forceinline__ void epilogue_role(const TmaMaps& maps, const GemmEpi
                         st_shared_v4(bufA + swz128(lane, q), __float_as_uint(x0), __float_as_uint(x1), __float_as_uint(x2),
                                      __float_as_uint(x3));
                     }
+                } else if (E::ce) {
+                    // the stored logits are fp16, not bf16 (common.cuh: pack_f16x2); same 2-byte tiles, same TMA store
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        st_shared_v4(bufA + slot_off + swz64(lane, q), pack_f16x2(p[q * 4 + 0]), pack_f16x2(p[q * 4 + 1]),
+                                     pack_f16x2(p[q * 4 + 2]), pack_f16x2(p[q * 4 + 3]));
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)

@@ -77,7 +77,8 @@ void ce_finalize(const float2* partial, int tiles, const float* target, const in
                  int M, cudaStream_t s);
 // loss = loss_sum / n_valid (NaN when no valid target, as the reference's mean over an empty set)
 void ce_loss(const float* loss_sum, const int* n_valid, float* loss_out, cudaStream_t s);
-// in place: z[r, v] <- (softmax(z[r])[v] - [v == label[r]]) / n_valid for valid rows, 0 otherwise / for v >= vocab
+// in place: z[r, v] (fp16 logits as the head's CE epilogue stores them) <- bf16 (softmax(z[r])[v] - [v == label[r]]) / n_valid for
+// valid rows, 0 otherwise / for v >= vocab
 void ce_dlogits(bf16* z, int ld, int M, int vocab, int n_cols, const float* lse, const int* label, const int* n_valid,
                 cudaStream_t s);
 

@@ -187,7 +187,8 @@ int eavqa_op_gemm(const void* A, int32_t lda, const void* B, int32_t ldb, int32_
  * read as MN-major UMMA operands, no transposed copies (dW = dY^T X of every trainable nn.Linear) */
 int eavqa_op_gemm_wgrad(const void* At, int32_t ldat, const void* Bt, int32_t ldbt, int32_t M, int32_t N, int32_t K, float* out,
                         int32_t ldo, int32_t block_n, void* stream);
-/* LM-head GEMM with fused softmax statistics: logits bf16 [M, ldo], lse [M] and target logit [M] */
+/* LM-head GEMM with fused softmax statistics: logits [M, ldo] as 2-byte fp16 values (they only feed d logits; fp16 is 8x finer
+ * than bf16 at trained-model logit magnitudes), lse [M] and target logit [M] */
 int eavqa_op_lmhead_ce(const void* H, const void* W, int32_t M, int32_t vocab, int32_t n_cols, int32_t K, const int32_t* label,
                        void* logits, int32_t ldo, float* lse, float* target, float* loss_sum, void* stream);
 int eavqa_op_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,

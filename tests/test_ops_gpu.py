@@ -247,7 +247,8 @@ def test_lmhead_ce(L, M):
     valid = label >= 0
     ref_t = ref.gather(1, label.clamp_min(0).long().unsqueeze(1)).squeeze(1)
     assert (target[valid] - ref_t[valid]).abs().max().item() < 2e-3
-    assert (logits[:, :V].float() - ref).abs().max().item() < 2e-3 + 2 ** -8 * ref.abs().max().item()
+    # the stored logits are fp16 bit patterns in the 2-byte buffer (they only feed d logits; common.cuh: pack_f16x2)
+    assert (logits.view(torch.float16)[:, :V].float() - ref).abs().max().item() < 2e-3 + 2 ** -11 * ref.abs().max().item()
     ref_loss = (ref_lse - ref_t)[valid].sum().item()
     assert abs(loss_sum.item() - ref_loss) < 1e-3 * abs(ref_loss)
 

@@ -166,6 +166,30 @@ def test_step_is_deterministic_and_scales_with_upstream_gradient():
     assert torch.allclose(g3, 2 * g1, rtol=1e-4, atol=1e-6 * float(g1.abs().max()))
 
 
+@pytest.mark.parametrize("gain", [1.0, 60.0])
+def test_train_step_parity_at_real_logit_scale(gain):
+    """Synthetic N(0, 0.02) weights give O(1) logits; a trained GPT-2 has |logit| of 30-150, where the rounding of the
+    STORED logits (they feed d logits = softmax - onehot in the backward) matters.  Scaling ln_f's gain lifts the tiny LM's
+    logits to that range (std ~ gain * 0.25): same bars as everywhere else against the live fp32 oracle."""
+    case = CASES["train_tiny_transformer"]
+    lm_w, mapper_w, batch, cfg = build_case(case)
+    lm_w = dict(lm_w)
+    lm_w["transformer.ln_f.weight"] = lm_w["transformer.ln_f.weight"] * gain
+    lm_w["transformer.ln_f.bias"] = lm_w["transformer.ln_f.bias"] * gain
+    model = build_model(case, lm_w, mapper_w)
+    out = model(question_tokens=batch["input_ids"], labels=batch["labels"], prefix=batch["clip_embeddings"],
+                question_mask=batch["attention_mask"], return_logits=True)
+    out.loss.backward()
+    loss_o, grads_o = orc.train_step(lm_w, mapper_w, cfg, batch["input_ids"], batch["clip_embeddings"], batch["attention_mask"], batch["labels"])
+    got = torch.cat([p.grad.flatten() for p in model.parameters()])
+    ref = torch.cat([grads_o[k].flatten() for k in grads_o])
+    cos = cosine(got, ref)
+    print(f"\n[logit scale x{gain:g}] |logit| max {float(out.logits.abs().max()):.1f} std {float(out.logits.std()):.2f}; loss {float(out.loss):.5f} "
+          f"oracle {loss_o:.5f}; grad cos {cos:.6f}")
+    assert abs(float(out.loss) - loss_o) <= LOSS_RTOL * abs(loss_o)
+    assert cos >= GRAD_COS, cos
+
+
 def test_flat_adamw_follows_schedulers_and_accumulates_micro_batches():
     """``FlatAdamW`` against ``torch.optim.AdamW`` on the same model through two optimiser steps of two micro-batches each
     (Lightning ``accumulate_grad_batches=2``, README.md:199-206) under a warm-up scheduler that drives ``param_groups`` --
