@@ -258,6 +258,8 @@ Engine::~Engine() {
     if (side_) cudaStreamDestroy(side_);
     for (void* p : owned_) cudaFree(p);
     if (host_flags_) cudaFreeHost(host_flags_);
+    if (dec_graph_) cudaGraphExecDestroy(dec_graph_);
+    if (dec_stream_) cudaStreamDestroy(dec_stream_);
 }
 
 int64_t Engine::pofs(const std::string& name) const {
@@ -760,6 +762,10 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     const bool chain_env = chain_opt != nullptr && chain_opt[0] == '1';
     const bool use_chain = chain_env && max_new > 1 && B <= 128 && d % 64 == 0 && decode_chain_supported(Tmax);
     const int n_chain = 1 + 7 * L;
+    // tokens / winning logits / picked-token log-probabilities are produced into engine-owned staging and copied out at the end:
+    // the decode graph bakes its pointers, the caller's tensors move from call to call
+    int64_t* tok_stage = nullptr;
+    float *top_stage = nullptr, *lp_stage = nullptr;
     ChainPhase* chain_dev = nullptr;
     unsigned* chain_bar = nullptr;
     unsigned long long* chain_trace = nullptr;
@@ -782,6 +788,9 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         acc_qkv = a.get<float>(static_cast<size_t>(B) * 3 * d); acc_o = a.get<float>(static_cast<size_t>(B) * d);
         acc_pr = a.get<float>(static_cast<size_t>(B) * d);
         kv = a.get<bf16>(kv_layer * L);
+        tok_stage = a.get<int64_t>(static_cast<size_t>(B) * max_new);
+        top_stage = a.get<float>(static_cast<size_t>(B) * max_new);
+        lp_stage = a.get<float>(static_cast<size_t>(B) * max_new);
         chain_dev = a.get<ChainPhase>(n_chain);
         chain_bar = a.get<unsigned>(1);
         chain_trace = a.get<unsigned long long>(9 + 2 * n_chain);
@@ -838,14 +847,16 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
     launch_kernel(last_row_index_kernel, dim3(ceil_div(B, 256)), dim3(256), 0, s, row_index, B, T0);
     KERNEL_CHECK();
     count_launch();
-    auto head_and_pick = [&](int step) {       // hc = ln_f(last hidden) -> logits -> greedy token, next input embedding in x_a
-        gemm(hc, d, wte_bf16_, d, B, Vpad_, d, ep_f32(logits, Vpad_), s);
-        greedy_step(logits, Vpad_, B, V_, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out, n_unfinished,
-                    top_logit, token_logprob, wte_f32_, wpe_f32_ + static_cast<size_t>(std::min(T0 + step, cfg_.n_positions - 1)) * d, d, x_a,
-                    validD + T0 + step, Tmax, part_val, part_idx, arrivals, s);
+    float* const top_dst = top_logit ? top_stage : nullptr;
+    float* const lp_dst = token_logprob ? lp_stage : nullptr;
+    auto head_and_pick = [&](int step, cudaStream_t st) {   // hc = ln_f(last hidden) -> logits -> greedy token, next input embedding in x_a
+        gemm(hc, d, wte_bf16_, d, B, Vpad_, d, ep_f32(logits, Vpad_), st);
+        greedy_step(logits, Vpad_, B, V_, step, max_new, has_eos, pad_id, eos_id, unfinished, tok_stage, n_unfinished,
+                    top_dst, lp_dst, wte_f32_, wpe_f32_ + static_cast<size_t>(std::min(T0 + step, cfg_.n_positions - 1)) * d, d, x_a,
+                    validD + T0 + step, Tmax, part_val, part_idx, arrivals, st);
     };
     layernorm_fwd(ha, d, row_index, lnf_g_, lnf_b_, hc, d, nullptr, nullptr, B, d, 1e-5f, s);
-    head_and_pick(0);
+    head_and_pick(0, s);
 
     // ---- decode: one token per row per step against the KV cache (the reference re-runs the whole sequence each
     //      step, clipcap.py:416-419; same function, 11x less work).  M = B rows per GEMM: every projection is split along K
@@ -881,34 +892,84 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
             // the head (B x Vpad x d, 100 MB of weights) runs on the wide-tile stand-alone GEMM: at 64-column tiles the chain
             // would re-read the 128 activation rows once per tile (measured 36 us against ~20)
             gemm(hc, d, wte_bf16_, d, B, Vpad_, d, ep_f32(logits, Vpad_), s);
-            greedy_step(logits, Vpad_, B, V_, step, max_new, has_eos, pad_id, eos_id, unfinished, tokens_out, n_unfinished, top_logit,
-                        token_logprob, wte_f32_, wpe_f32_ + static_cast<size_t>(std::min(T0 + step, cfg_.n_positions - 1)) * d, d, x_a,
+            greedy_step(logits, Vpad_, B, V_, step, max_new, has_eos, pad_id, eos_id, unfinished, tok_stage, n_unfinished, top_dst,
+                        lp_dst, wte_f32_, wpe_f32_ + static_cast<size_t>(std::min(T0 + step, cfg_.n_positions - 1)) * d, d, x_a,
                         validD + T0 + step, Tmax, part_val, part_idx, arrivals, s);
         }
     }
-    for (int step = 1; step < max_new && !use_chain; ++step) {
-        const int pos = T0 + step - 1;
-        decode_residual_ln(x_a, nullptr, nullptr, layers_[0].ln1_g, layers_[0].ln1_b, u, B, d, 1e-5f, acc_qkv, 3 * d, s);
-        for (int l = 0; l < L; ++l) {
-            const LmLayer& w = layers_[l];
-            gemm_decode(u, d, w.w_qkv_t, d, B, 3 * d, d, acc_qkv, s);
-            lm_attention_decode_acc(acc_qkv, w.b_qkv, kv + kv_layer * l, validD, Tmax, att, acc_o, B, H_, pos, Tmax, s);
-            gemm_decode(att, d, w.w_o_t, d, B, d, d, acc_o, s);
-            decode_residual_ln(x_a, acc_o, w.b_o, w.ln2_g, w.ln2_b, u, B, d, 1e-5f, acc_pr, d, s);
-            {   // c_fc has 4d / 64 = 64+ tiles of its own: unsplit with the fused bias + gelu epilogue beats split-K plus a
-                // separate gelu kernel (8.3 us vs 6.6 + 6.2 us per layer)
-                GemmEpilogue e = ep_bf16(fc_act, 4 * d, w.b_fc);
-                e.act = ACT_GELU_NEW;
-                gemm(u, d, w.w_fc_t, d, B, 4 * d, d, e, s, 64);
+    auto decode_loop = [&](cudaStream_t st) {
+        for (int step = 1; step < max_new; ++step) {
+            const int pos = T0 + step - 1;
+            decode_residual_ln(x_a, nullptr, nullptr, layers_[0].ln1_g, layers_[0].ln1_b, u, B, d, 1e-5f, acc_qkv, 3 * d, st);
+            for (int l = 0; l < L; ++l) {
+                const LmLayer& w = layers_[l];
+                gemm_decode(u, d, w.w_qkv_t, d, B, 3 * d, d, acc_qkv, st);
+                lm_attention_decode_acc(acc_qkv, w.b_qkv, kv + kv_layer * l, validD, Tmax, att, acc_o, B, H_, pos, Tmax, st);
+                gemm_decode(att, d, w.w_o_t, d, B, d, d, acc_o, st);
+                decode_residual_ln(x_a, acc_o, w.b_o, w.ln2_g, w.ln2_b, u, B, d, 1e-5f, acc_pr, d, st);
+                {   // c_fc has 4d / 64 = 64+ tiles of its own: unsplit with the fused bias + gelu epilogue beats split-K plus a
+                    // separate gelu kernel (8.3 us vs 6.6 + 6.2 us per layer)
+                    GemmEpilogue e = ep_bf16(fc_act, 4 * d, w.b_fc);
+                    e.act = ACT_GELU_NEW;
+                    gemm(u, d, w.w_fc_t, d, B, 4 * d, d, e, st, 64);
+                }
+                gemm_decode(fc_act, 4 * d, w.w_pr_t, 4 * d, B, d, 4 * d, acc_pr, st);
+                if (l + 1 < L)
+                    decode_residual_ln(x_a, acc_pr, w.b_pr, layers_[l + 1].ln1_g, layers_[l + 1].ln1_b, u, B, d, 1e-5f, acc_qkv, 3 * d, st);
+                else
+                    decode_residual_ln(x_a, acc_pr, w.b_pr, lnf_g_, lnf_b_, hc, B, d, 1e-5f, nullptr, 0, st);
             }
-            gemm_decode(fc_act, 4 * d, w.w_pr_t, 4 * d, B, d, 4 * d, acc_pr, s);
-            if (l + 1 < L)
-                decode_residual_ln(x_a, acc_pr, w.b_pr, layers_[l + 1].ln1_g, layers_[l + 1].ln1_b, u, B, d, 1e-5f, acc_qkv, 3 * d, s);
-            else
-                decode_residual_ln(x_a, acc_pr, w.b_pr, lnf_g_, lnf_b_, hc, B, d, 1e-5f, nullptr, 0, s);
+            head_and_pick(step, st);
         }
-        head_and_pick(step);
+    };
+    if (!use_chain && max_new > 1) {
+        // The decode loop replayed as ONE CUDA graph (EAVQA_DECODE_GRAPH=0 turns it off; measured 24.46 -> 24.08 ms per
+        // 128-answer batch: the steps are bound by their chain of memory round trips, not by launch cost, so the gain is the
+        // ~1.5 % of host / front-end overhead).  The first call with a new (shape, arena placement)
+        // runs the launches directly (kernel attributes, tensor maps, workspace growth all settle); the second captures them
+        // on the engine's own stream (the caller's may be the legacy default stream, which cannot be captured); later calls
+        // only launch the instantiated graph.  Programmatic-dependent-launch attributes are kept as programmatic edges.
+        const char* gopt = getenv("EAVQA_DECODE_GRAPH");
+        const bool want_graph = !(gopt != nullptr && gopt[0] == '0') && !gemm_profile_active();
+        DecodeGraphKey key;
+        key.B = B; key.T0 = T0; key.max_new = max_new; key.has_eos = has_eos; key.want_top = top_logit != nullptr;
+        key.want_lp = token_logprob != nullptr; key.pad_id = pad_id; key.eos_id = eos_id; key.arena_base = arena_.base();
+        if (!want_graph || !(key == dec_seen_)) {
+            dec_seen_ = key;
+            decode_loop(s);
+        } else {
+            if (dec_graph_ == nullptr || !(key == dec_key_)) {
+                if (dec_graph_ != nullptr) {
+                    CUDA_CHECK(cudaGraphExecDestroy(dec_graph_));
+                    dec_graph_ = nullptr;
+                }
+                if (dec_stream_ == nullptr) CUDA_CHECK(cudaStreamCreateWithFlags(&dec_stream_, cudaStreamNonBlocking));
+                const int64_t before = kernel_launch_count() + gemm_launch_count();
+                cudaGraph_t graph = nullptr;
+                CUDA_CHECK(cudaStreamBeginCapture(dec_stream_, cudaStreamCaptureModeThreadLocal));
+                try {
+                    decode_loop(dec_stream_);
+                } catch (...) {
+                    cudaStreamEndCapture(dec_stream_, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    throw;
+                }
+                CUDA_CHECK(cudaStreamEndCapture(dec_stream_, &graph));
+                CUDA_CHECK(cudaGraphInstantiate(&dec_graph_, graph, 0));
+                CUDA_CHECK(cudaGraphDestroy(graph));
+                dec_graph_launches_ = static_cast<int>(kernel_launch_count() + gemm_launch_count() - before);
+                dec_key_ = key;
+            } else {
+                count_launch(dec_graph_launches_);
+            }
+            CUDA_CHECK(cudaGraphLaunch(dec_graph_, s));
+        }
     }
+    // results leave the staging buffers (the caller's tensors are not baked into anything)
+    CUDA_CHECK(cudaMemcpyAsync(tokens_out, tok_stage, sizeof(int64_t) * static_cast<size_t>(B) * max_new, cudaMemcpyDeviceToDevice, s));
+    if (top_logit) CUDA_CHECK(cudaMemcpyAsync(top_logit, top_stage, sizeof(float) * static_cast<size_t>(B) * max_new, cudaMemcpyDeviceToDevice, s));
+    if (token_logprob)
+        CUDA_CHECK(cudaMemcpyAsync(token_logprob, lp_stage, sizeof(float) * static_cast<size_t>(B) * max_new, cudaMemcpyDeviceToDevice, s));
     CUDA_CHECK(cudaMemcpyAsync(host_flags_, flags, sizeof(int) * (max_new + 1), cudaMemcpyDeviceToHost, s));
     static const bool timing = getenv("EAVQA_TIMING") != nullptr;
     const auto t_enq = std::chrono::steady_clock::now();

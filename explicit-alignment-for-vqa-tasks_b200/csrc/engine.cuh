@@ -28,6 +28,7 @@ public:
     void* alloc(size_t bytes);
     template <typename T> T* get(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
     size_t capacity() const { return cap_; }
+    const void* base() const { return base_; }
     size_t used() const { return off_; }
 private:
     uint8_t* base_ = nullptr;
@@ -109,6 +110,21 @@ private:
     void join(cudaStream_t main);           // `main` waits for the side stream
     int32_t* host_flags_ = nullptr;      // pinned: n_unfinished[max] + err flag read-back
     int host_flags_cap_ = 0;
+    // The single-token steps of generate() as a CUDA graph (on unless EAVQA_DECODE_GRAPH=0): the ~1500 launches of steps 1..max_new-1
+    // are captured once per (shape, arena placement) on an engine-owned stream and replayed with one cudaGraphLaunch.
+    struct DecodeGraphKey {
+        int B = 0, T0 = 0, max_new = 0, has_eos = 0, want_top = 0, want_lp = 0;
+        int64_t pad_id = 0, eos_id = 0;
+        const void* arena_base = nullptr;
+        bool operator==(const DecodeGraphKey& o) const {
+            return B == o.B && T0 == o.T0 && max_new == o.max_new && has_eos == o.has_eos && want_top == o.want_top && want_lp == o.want_lp &&
+                   pad_id == o.pad_id && eos_id == o.eos_id && arena_base == o.arena_base;
+        }
+    };
+    DecodeGraphKey dec_key_, dec_seen_;
+    cudaGraphExec_t dec_graph_ = nullptr;
+    int dec_graph_launches_ = 0;         // kernels inside the captured graph (for eavqa_launch_count)
+    cudaStream_t dec_stream_ = nullptr;
 };
 
 }  // namespace eavqa

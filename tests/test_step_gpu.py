@@ -332,6 +332,31 @@ def test_persistent_decode_kernel_equals_the_launch_per_operation_path(name, mon
     assert agree >= len(tok0) - (0 if case.get("successor") else 1), (tok1, tok0)
 
 
+@pytest.mark.parametrize("name", ["gen_tiny_fewshot_chain", "gen_gpt2_prepend_chain"])
+def test_decode_graph_replay_equals_direct_launches(name, monkeypatch):
+    """By default (EAVQA_DECODE_GRAPH != 0) the single-token steps are captured once per shape and replayed with one cudaGraphLaunch: the
+    first call launches directly, the second captures, the third and fourth replay -- all four must give the answers and
+    winning logits of the plain path, also when the caller's output tensors move between calls."""
+    case = CASES[name]
+    lm_w, mapper_w, batch, cfg = build_case(case)
+    model = build_model(case, lm_w, mapper_w).eval()
+    kw = dict(question_tokens=batch["input_ids"], prefix=batch["clip_embeddings"], question_mask=batch["attention_mask"],
+              max_length=case["max_length"], pad_token_id=case["pad_token_id"], eos_token_id=case["eos_token_id"])
+    monkeypatch.setenv("EAVQA_DECODE_GRAPH", "0")
+    tok0, top0 = model.generate(return_top_logits=True, **kw)
+    monkeypatch.setenv("EAVQA_DECODE_GRAPH", "1")
+    keep = []
+    for _ in range(4):
+        tok, top = model.generate(return_top_logits=True, **kw)
+        keep.append(torch.empty(1 << 16, device="cuda"))          # shifts the allocator: the next call's outputs live elsewhere
+        assert tok == tok0
+        assert (top - top0).abs().max().item() <= 2e-3 * (1.0 + top0.abs().max().item())
+    lp = model.generate(return_logprobs=True, **kw)[1]              # a different set of outputs: its own graph
+    lp2 = model.generate(return_logprobs=True, **kw)[1]
+    lp3 = model.generate(return_logprobs=True, **kw)[1]
+    assert torch.allclose(lp, lp2, atol=5e-3) and torch.allclose(lp, lp3, atol=5e-3)
+
+
 def test_generate_api_shapes_and_errors():
     case = CASES["gen_tiny_fewshot"]
     lm_w, mapper_w, batch, cfg = build_case(case)
