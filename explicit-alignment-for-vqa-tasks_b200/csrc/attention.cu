@@ -9,6 +9,7 @@
 //  * mapper_attention_{fwd,bwd}: the mapper's 8-head, unmasked self-attention over S = 20 rows
 //    (clipcap.py:81-104); fp32 CUDA-core math in shared memory.
 #include <algorithm>
+#include <atomic>
 
 #include "kernels.cuh"
 
@@ -1391,7 +1392,7 @@ __global__ void __launch_bounds__(128) mapper_attention_bwd_kernel(const bf16* _
 void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, int B, int T, int H, cudaStream_t s, bf16* kv_cache,
                       int Tmax) {
     if (T <= BLK && kv_cache == nullptr) {
-        static bool configured = false;
+        static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
         if (!configured) {
             CUDA_CHECK(cudaFuncSetAttribute(lm_attention_fwd_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFwdSetBytes));
             configured = true;
@@ -1413,7 +1414,7 @@ void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, in
 void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf16* d_o, const float* lse, bf16* dqkv,
                       float* dq_scratch, int B, int T, int H, cudaStream_t s) {
     const int smem = 6 * BLK * LDS * sizeof(bf16) + 2 * BLK * sizeof(float) + BLK * sizeof(int);
-    static bool configured = false;
+    static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(lm_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -1421,7 +1422,7 @@ void lm_attention_bwd(const bf16* qkv, const int* valid, const bf16* o, const bf
     EAVQA_CHECK(T <= BLK || dq_scratch != nullptr, "lm_attention_bwd needs dq_scratch for T > 64");
     dim3 grid(H, B);
     if (T <= BLK) {
-        static bool configured1 = false;
+        static std::atomic<bool> configured1{false};
         if (!configured1) {
             CUDA_CHECK(cudaFuncSetAttribute(lm_attention_bwd_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured1 = true;
@@ -1442,7 +1443,7 @@ void lm_attention_decode_acc(const float* qkv_acc, const float* qkv_bias, bf16* 
     const int n = pos + 1;
     if (n <= kDecodeStageKeys) {
         const size_t smem = static_cast<size_t>(n) * (2 * HD * sizeof(bf16) + sizeof(float) + sizeof(int));
-        static bool configured = false;
+        static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
         if (!configured) {
             CUDA_CHECK(cudaFuncSetAttribute(lm_attention_decode_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             kDecodeStageKeys * (2 * HD * static_cast<int>(sizeof(bf16)) + 2 * static_cast<int>(sizeof(float)))));
@@ -1463,7 +1464,7 @@ void lm_attention_decode_acc(const float* qkv_acc, const float* qkv_bias, bf16* 
 template <int HDIM>
 static void launch_mapper_bwd_mma(const bf16* qkv, const bf16* d_o, bf16* dqkv, int B, int S, int H, cudaStream_t s) {
     const int smem = (4 * 32 * (HDIM + 8) + 2 * 32 * 40) * sizeof(bf16);
-    static bool configured = false;
+    static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured && smem > 48 * 1024) {
         CUDA_CHECK(cudaFuncSetAttribute(mapper_attention_bwd_mma_kernel<HDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;

@@ -12,6 +12,7 @@
 // Data crossing a phase boundary lives in global memory (L2): generic-proxy writers fence towards the async proxy before
 // the barrier, the TMA producer fences after it; bulk stores are waited for (complete, not just read) before the barrier.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <vector>
 
@@ -610,7 +611,7 @@ void chain_glue_phase(ChainPhase& p, float* x, const float* acc, const float* bi
 
 void launch_decode_chain(const ChainPhase* dev_phases, int n_phases, int pos, unsigned* bar_counter, unsigned epoch0, cudaStream_t s,
                          unsigned long long* trace) {
-    static bool configured = false;
+    static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(dc::decode_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::SMEM));
         configured = true;

@@ -18,6 +18,7 @@
 // ~620 warp-instructions per 32-column chunk.  Compile-time modes + packed f32x2 math (FADD2/FMUL2/FFMA2) +
 // ping-pong tcgen05.ld register blocks bring the gelu + two-output epilogue to ~190.
 #pragma once
+#include <atomic>
 #include <string>
 
 #include "gemm.cuh"
@@ -793,7 +794,7 @@ inline void launch_with_attrs(Kernel kernel, int grid, int smem, int cluster, cu
 template <int BN, int MODE, bool MN>
 void launch_1cta(const GemmArgs& a, cudaStream_t stream) {
     using C = Cfg<BN>;
-    static bool configured = false;
+    static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
@@ -819,7 +820,7 @@ void launch_1cta(const GemmArgs& a, cudaStream_t stream) {
 template <int BN, int MODE>
 void launch_2cta(const GemmArgs& a, cudaStream_t stream) {
     using C = Cfg2<BN>;
-    static bool configured = false;
+    static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;

@@ -15,6 +15,7 @@
 // running k-th-score threshold: after the first chunks almost nothing passes the threshold, so selection costs one
 // streaming read of the tile.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <vector>
 
@@ -302,7 +303,7 @@ void rices_search(const float* queries, const float* database, int64_t M, int64_
     const int cap = select_cap(k);
     const int P = 1 << static_cast<int>(std::ceil(std::log2(static_cast<double>(cap))));
     const size_t sel_smem = sizeof(Cand) * static_cast<size_t>(P);
-    static bool configured = false;
+    static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(rices_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CUDA_CHECK(cudaFuncSetAttribute(rices_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -362,7 +363,7 @@ void rices_rerank(const float* query, const float* table, int64_t M, int D, cons
     EAVQA_CHECK(query && table && cand && out_sim && out_pos, "rices_rerank: null argument");
     EAVQA_CHECK(M > 0 && D > 0 && C >= 1 && C <= 4096, "rices_rerank: bad shape (1 <= candidates <= 4096)");
     const int P = 1 << static_cast<int>(std::ceil(std::log2(static_cast<double>(C))));
-    static bool configured = false;
+    static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(rices_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         configured = true;
