@@ -3,8 +3,8 @@
     ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file launches.csv python tools/gen_bench.py 1
     python tools/ncu_generate_summary.py launches.csv
 
-The call = the launches from the last mapper weight packing (`pack_batch_kernel`, first kernel of a generate call) to the
-end of the list.  ncu serialises launches with cold caches: compare shares, not absolute times.
+A call starts at a mapper weight packing (`pack_batch_kernel`); the last call with the most launches is summarised
+(bench_generate ends with prefill-only calls).  Run with EAVQA_DECODE_GRAPH=0 so that the steps are plain launches.  ncu serialises launches with cold caches: compare shares, not absolute times.
 """
 import collections
 import csv
@@ -16,7 +16,10 @@ lines = [l for l in open(path) if not l.startswith("==")]
 recs = list(csv.DictReader(lines))
 names = [x["Kernel Name"] for x in recs]
 starts = [i for i, n in enumerate(names) if "pack_batch" in n]
-call = recs[starts[-1]:] if starts else recs
+# bench_generate ends with prefill-only calls (max_length = 1, its roofline split): take the last FULL call
+segs = [recs[a:b] for a, b in zip(starts, starts[1:] + [len(recs)])] if starts else [recs]
+longest = max(len(x) for x in segs)
+call = [x for x in segs if len(x) == longest][-1]
 agg = collections.defaultdict(lambda: [0.0, 0])
 for x in call:
     n = re.sub(r"\(.*", "", x["Kernel Name"])
