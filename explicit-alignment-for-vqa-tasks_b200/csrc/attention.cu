@@ -239,6 +239,153 @@ __global__ void __launch_bounds__(128, 4) lm_attention_fwd_kernel(const bf16* __
     }
 }
 
+// Generation prefill with up to three key blocks (T <= 192: the few-shot prompts, T0 ~ 125-145): ONE CTA per (sample, head)
+// keeps the head's K and V resident in shared memory and walks its query blocks, so K / V are read once (the general kernel
+// above runs one CTA per query block and re-reads the key blocks below the diagonal: 6 block pairs instead of 3 at T = 143;
+// round-2 launch list: 88 us per layer, 19 % of the prefill), the next query tile streams in while the current one is
+// reduced, the KV cache is filled from the resident tiles and O leaves as 16-byte row-contiguous stores.
+constexpr int kPrefillMaxBlocks = 3;
+__global__ void __launch_bounds__(128, 3) lm_attention_prefill_kernel(const bf16* __restrict__ qkv, const int* __restrict__ valid,
+                                                                   bf16* __restrict__ o, int T, int H, bf16* __restrict__ kv_cache,
+                                                                   int Tmax) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ __align__(16) uint8_t pre_smem[];
+    const int nblk = (T + BLK - 1) / BLK;
+    bf16* Ks = reinterpret_cast<bf16*>(pre_smem);                       // [nblk * 64][LDS]
+    bf16* Vs = Ks + nblk * BLK * LDS;
+    bf16* Qs0 = Vs + nblk * BLK * LDS;                                  // two query tiles
+    int* kvalid = reinterpret_cast<int*>(Qs0 + 2 * BLK * LDS);          // [nblk * 64]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int d = H * HD;
+    const int64_t ld = 3 * d;
+    const bf16* base = qkv + static_cast<int64_t>(b) * T * ld + h * HD;
+    const float scale = 0.125f;
+
+    for (int kb = 0; kb < nblk; ++kb) {
+        load_tile_async(Ks + kb * BLK * LDS, base + d, ld, kb * BLK, T, tid);
+        load_tile_async(Vs + kb * BLK * LDS, base + 2 * d, ld, kb * BLK, T, tid);
+    }
+    for (int t = tid; t < nblk * BLK; t += 128) {
+        if (t < T) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(kvalid + t)), "l"(valid + b * T + t) : "memory");
+        else kvalid[t] = 0;
+    }
+    load_tile_async(Qs0, base, ld, 0, T, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    for (int qb = 0; qb < nblk; ++qb) {
+        bf16* Qs = Qs0 + (qb & 1) * BLK * LDS;
+        const int q0 = qb * BLK;
+        cp_async_wait_all();
+        __syncthreads();                          // tile qb (and, first time, K / V / validity) visible; the other q tile is free
+        if (qb + 1 < nblk) {
+            load_tile_async(Qs0 + ((qb + 1) & 1) * BLK * LDS, base, ld, q0 + BLK, T, tid);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        if (qb == 0 && kv_cache != nullptr) {     // fill the head-major KV cache from the resident tiles
+            const int nb = gridDim.y;
+            bf16* kc = kv_cache + (static_cast<int64_t>(b) * H + h) * Tmax * HD;
+            bf16* vc = kc + static_cast<int64_t>(nb) * H * Tmax * HD;
+            for (int idx = tid; idx < T * 8; idx += 128) {
+                const int r = idx >> 3, c = (idx & 7) * 8;
+                *reinterpret_cast<uint4*>(kc + static_cast<int64_t>(r) * HD + c) = *reinterpret_cast<const uint4*>(Ks + r * LDS + c);
+                *reinterpret_cast<uint4*>(vc + static_cast<int64_t>(r) * HD + c) = *reinterpret_cast<const uint4*>(Vs + r * LDS + c);
+            }
+        }
+        uint32_t qf[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) load_a(qf[ks], Qs, warp * 16, ks * 16, lane);
+        float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
+        float oacc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oacc[i][e] = 0.f;
+        for (int kb = 0; kb <= qb; ++kb) {
+            const int k0 = kb * BLK;
+            const bf16* Kt = Ks + kb * BLK * LDS;
+            const bf16* Vt = Vs + kb * BLK * LDS;
+            float sacc[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sacc[i][e] = 0.f;
+            warp_gemm_nt(sacc, qf, Kt, lane);
+            float rmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = nt * 8 + 2 * t4 + (e & 1);
+                    const int row = warp * 16 + g + ((e >> 1) << 3);
+                    const bool ok = kvalid[k0 + col] && (k0 + col <= q0 + row);
+                    const float sv = ok ? sacc[nt][e] * scale : -INFINITY;
+                    sacc[nt][e] = sv;
+                    rmax[e >> 1] = fmaxf(rmax[e >> 1], sv);
+                }
+            float alpha[2], muse[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 1));
+                rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 2));
+                const float mn = fmaxf(m_i[r], rmax[r]);
+                muse[r] = (mn == -INFINITY) ? 0.f : mn;
+                alpha[r] = __expf(m_i[r] - muse[r]);
+                m_i[r] = mn;
+                l_i[r] *= alpha[r];
+            }
+            uint32_t pf[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float p0 = __expf(sacc[nt][0] - muse[0]), p1 = __expf(sacc[nt][1] - muse[0]);
+                const float p2 = __expf(sacc[nt][2] - muse[1]), p3 = __expf(sacc[nt][3] - muse[1]);
+                l_i[0] += p0 + p1;
+                l_i[1] += p2 + p3;
+                pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+                pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                oacc[i][0] *= alpha[0]; oacc[i][1] *= alpha[0];
+                oacc[i][2] *= alpha[1]; oacc[i][3] *= alpha[1];
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                for (int np = 0; np < 4; ++np) {
+                    uint32_t bfr[4];
+                    load_b_trans(bfr, Vt, np * 16, ks * 16, lane);
+                    mma_bf16(oacc[2 * np], pf[ks], bfr[0], bfr[1]);
+                    mma_bf16(oacc[2 * np + 1], pf[ks], bfr[2], bfr[3]);
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
+            l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
+        }
+        // O through this warp's own 16 rows of the query tile, then 16-byte row-contiguous stores
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = warp * 16 + g + r * 8;
+            const float inv = l_i[r] > 0.f ? 1.0f / l_i[r] : 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+                *reinterpret_cast<uint32_t*>(Qs + row * LDS + nt * 8 + 2 * t4) = pack_bf16x2(oacc[nt][2 * r] * inv, oacc[nt][2 * r + 1] * inv);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = warp * 16 + (lane >> 3) + 4 * i, c = (lane & 7) * 8;
+            if (q0 + row < T)
+                *reinterpret_cast<uint4*>(o + (static_cast<int64_t>(b) * T + q0 + row) * d + h * HD + c) = *reinterpret_cast<const uint4*>(Qs + row * LDS + c);
+        }
+    }
+}
+
 // Sequences of at most one block (T <= 64: the training step, T = 50): PERSISTENT CTAs walk the (sample, head) items with
 // the next item's q / k / v tiles and validity words already streaming into a second buffer set while the current item is
 // reduced, and O leaves through shared memory as 16-byte coalesced stores.  Round-2 reason: the one-CTA-per-item kernel above
@@ -1400,6 +1547,20 @@ void lm_attention_fwd(const bf16* qkv, const int* valid, bf16* o, float* lse, in
         const int n_items = B * H;
         launch_kernel(lm_attention_fwd_single_kernel, dim3(std::min(n_items, 4 * num_sms())), dim3(128), 2 * kFwdSetBytes, s, qkv, valid, o,
                       lse, T, H, n_items);
+        KERNEL_CHECK();
+        count_launch();
+        return;
+    }
+    if (lse == nullptr && T > BLK && T <= kPrefillMaxBlocks * BLK) {
+        const int nblk = ceil_div(T, BLK);
+        const size_t smem = static_cast<size_t>(2 * nblk + 2) * BLK * LDS * sizeof(bf16) + static_cast<size_t>(nblk) * BLK * sizeof(int);
+        static std::atomic<bool> configured{false};
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(lm_attention_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (2 * kPrefillMaxBlocks + 2) * BLK * LDS * static_cast<int>(sizeof(bf16)) + kPrefillMaxBlocks * BLK * 4));
+            configured = true;
+        }
+        launch_kernel(lm_attention_prefill_kernel, dim3(H, B), dim3(128), smem, s, qkv, valid, o, T, H, kv_cache, Tmax);
         KERNEL_CHECK();
         count_launch();
         return;
