@@ -205,6 +205,9 @@ def main():
     ap.add_argument("--only-timed", action="store_true", help="run only warm-up + the timed region (for ncu launch lists)")
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="N > 1: bucketed gradient all-reduce overlapped with the mapper backward instead of one all-reduce after the step")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: 'fused' = ONE kernel per rank does reduce-scatter + AdamW + all-gather over NVLink peer / multicast "
+                         "memory (eavqa_sharded_adamw_step); 'nccl' = NCCL all-reduce of the flat gradient, then the fused AdamW on every rank")
     ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: cap on NCCL's CTAs per collective (0 = NCCL's default)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the headline): 256 samples per GPU; strong: 256 samples in total, 256 / N per GPU (SURVEY.md 8d)")
@@ -270,15 +273,28 @@ def main():
     host = syn.make_caption_batch(B, W["text_len"], W["clip_dim"], W["vocab"], seed=2021 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
-    opt = FlatAdamW(model, lr=1e-4)
-    from eavqa_b200.parallel import OverlappedGradReducer
+    from eavqa_b200.parallel import NvlinkShardedAdamW, OverlappedGradReducer
+    global ALLREDUCE_NOTE
+    opt, fused = None, False
+    if world > 1 and args.exchange == "fused" and not args.overlap_allreduce:
+        # the exchange step and the optimiser as ONE kernel per rank over NVLink / NVSwitch peer memory (csrc/collective.cu).
+        # Measured (profiles/README.md, round 2): N = 2 0.277 ms against 0.535 ms for NCCL all-reduce + AdamW.
+        try:
+            opt = NvlinkShardedAdamW(model, lr=1e-4)
+            fused = True
+            ALLREDUCE_NOTE = ("none: reduce-scatter + AdamW + all-gather fused in one kernel per rank (%s), barriers inside the kernel"
+                              % ("NVLS multimem.ld_reduce / multimem.st" if opt.multicast else "NVLink peer loads / stores"))
+        except Exception as e:      # symmetric memory unavailable on this box: the NCCL path below, and the line says so
+            print("[bench] fused exchange unavailable (%s: %s); using the NCCL all-reduce" % (type(e).__name__, e), file=sys.stderr)
+            opt = None
+    if opt is None:
+        opt = FlatAdamW(model, lr=1e-4)
     # --overlap-allreduce: bucketed all-reduce on a communication stream, started per pair of mapper layers while the rest of
     # the mapper backward runs.  Measured (profiles/README.md): N = 2 11.20 vs 11.34 ms/step for one all-reduce after the
     # step, N = 8 11.50 vs 11.26 ms/step (NVLS makes the 167 MB all-reduce cost only ~0.4 ms; NCCL's CTAs slow the GEMMs they
-    # overlap by about as much).  Default: one all-reduce of the whole flat buffer after the step.
+    # overlap by about as much).
     reducer = OverlappedGradReducer(model) if (world > 1 and args.overlap_allreduce) else None
-    global ALLREDUCE_NOTE
-    if world > 1:
+    if world > 1 and not fused:
         ALLREDUCE_NOTE = ("bucketed NCCL all-reduce overlapped with the mapper backward" if reducer is not None else
                           "one NCCL all-reduce of the flat fp32 mapper gradient after the step") + \
                          (", NCCL capped at %d CTAs" % args.nccl_max_ctas if args.nccl_max_ctas > 0 else "")
@@ -286,12 +302,15 @@ def main():
     def step(b):
         out = model(question_tokens=b["input_ids"], labels=b["labels"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"])
         out.loss.backward()
-        g = model.last_flat_grads
-        if reducer is not None:
-            reducer.reduce(g)
-        elif world > 1:
-            dist.all_reduce(g)                               # sum; the 1/W of the DDP mean is folded into AdamW
-        opt.step(g, grad_scale=1.0 / world)
+        if fused:
+            opt.step()                                       # sum over ranks, 1/W, AdamW, broadcast: one kernel
+        else:
+            g = model.last_flat_grads
+            if reducer is not None:
+                reducer.reduce(g)
+            elif world > 1:
+                dist.all_reduce(g)                           # sum; the 1/W of the DDP mean is folded into AdamW
+            opt.step(g, grad_scale=1.0 / world)
         opt.zero_grad()
         return out.loss
 

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeavqa_b200.so")
 SOURCES = ["gemm_inst_256.cu", "gemm_inst_192.cu", "gemm_inst_128.cu", "gemm_inst_64.cu", "gemm_tcgen05.cu", "elementwise.cu",
-           "attention.cu", "decode_chain.cu", "rices.cu", "engine.cu", "api.cu"]
+           "attention.cu", "decode_chain.cu", "rices.cu", "collective.cu", "engine.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "--use_fast_math",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

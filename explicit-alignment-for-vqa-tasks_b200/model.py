@@ -177,6 +177,7 @@ class ClipCaptionModelB200(nn.Module):
         self._slices: List[tuple] = []
         self._param_list: List[nn.Parameter] = []
         self.last_flat_grads = None
+        self._grad_buffer = None        # persistent flat gradient buffer (symmetric memory), see _adopt_flat
         self.save_lm = False           # state_dict() also emits the frozen LM (reference checkpoint layout) when True
 
     # ------------------------------------------------------------------ LM weights
@@ -257,6 +258,22 @@ class ClipCaptionModelB200(nn.Module):
             self._param_list.append(p)
             off += n
         self._flat = flat
+        self._grad_buffer = None        # a persistent gradient buffer belongs to the flat buffer it was adopted with
+
+    def _adopt_flat(self, new_flat: torch.Tensor, grad_buffer: Optional[torch.Tensor] = None):
+        """Move the flat parameter buffer into caller-provided storage of the same size (symmetric memory that peers can
+        address: ``parallel.NvlinkShardedAdamW``) and, optionally, make every backward write its flat gradient into
+        ``grad_buffer`` instead of a fresh allocation."""
+        self._ensure_engine()
+        if new_flat.shape != self._flat.shape or new_flat.dtype != torch.float32 or new_flat.device != self._flat.device:
+            raise ValueError("the new flat buffer must match the mapper's: %s fp32 on %s" % (tuple(self._flat.shape), self._flat.device))
+        new_flat.copy_(self._flat)
+        for p_, (o, n, shape) in zip(self._param_list, self._slices):
+            p_.data = new_flat[o:o + n].view(shape)
+        self._flat = new_flat
+        if grad_buffer is not None and (grad_buffer.shape != new_flat.shape or grad_buffer.dtype != torch.float32):
+            raise ValueError("the gradient buffer must have the flat parameter buffer's shape and dtype")
+        self._grad_buffer = grad_buffer
 
     def _params_are_flat(self) -> bool:
         if self._flat is None:
@@ -319,7 +336,9 @@ class ClipCaptionModelB200(nn.Module):
         L = _lib.load()
         B, Tt = tokens.shape
         loss = torch.empty((), dtype=torch.float32, device=self._flat.device)
-        grads = torch.empty_like(self._flat) if need_grad else None
+        grads = None
+        if need_grad:
+            grads = self._grad_buffer if self._grad_buffer is not None else torch.empty_like(self._flat)
         with torch.cuda.device(self._flat.device):
             _lib.check(L.eavqa_train_step(self._handle, B, Tt, clip.data_ptr(), tokens.data_ptr(), _lib.ptr(mask),
                                           labels.data_ptr(), self._flat.data_ptr(), _lib.ptr(grads), loss.data_ptr(),

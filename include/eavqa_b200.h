@@ -166,6 +166,25 @@ int eavqa_scale_grads(float* grads, int64_t n, const float* scale, void* stream)
 int eavqa_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 
+/* Data-parallel exchange step fused with the optimiser (replaces Lightning DDP's NCCL all-reduce of the mapper gradients,
+ * main.py:133-138, followed by torch.optim.AdamW on every rank, clipcap_exector.py:79-81): ONE kernel per rank does
+ * reduce-scatter + AdamW + all-gather over NVLink / NVSwitch peer memory.  Rank r owns elements
+ * [begin, end) = eavqa_sharded_adamw_range(n, r, world) of the flat buffer: it reads the SUM over ranks of that shard of the
+ * gradients (mc_grads != NULL: `multimem.ld_reduce` on the NVLS multicast address, reduced inside the switch; else peer
+ * loads summed in rank order), applies the AdamW update of eavqa_adamw_step with ITS shard of exp_avg / exp_avg_sq (full-size
+ * local buffers, only the shard is touched), and stores the updated parameters into EVERY rank's parameter buffer
+ * (`multimem.st`, or one peer store per rank).  grad_ptrs / param_ptrs / flag_ptrs [world]: rank r's buffer as mapped into
+ * this process (symmetric-memory allocations of the host side); flag_ptrs: 64 zero-initialised uint32 per rank used by the
+ * two barriers inside the kernel (all gradients final / all stores landed), `token` must grow by one per call, starting at 1;
+ * flag_ptrs == NULL: no barriers inside (the caller brackets the call with its own cross-GPU barriers).
+ * Every rank must make the call, on a stream ordered after its backward; the kernel completes only after all ranks' stores
+ * into this rank's parameters have landed.  n % 4 == 0, world <= 16. */
+int eavqa_sharded_adamw_range(int64_t n, int32_t rank, int32_t world, int64_t* begin, int64_t* end);
+int eavqa_sharded_adamw_step(void* const* grad_ptrs, void* const* param_ptrs, const void* mc_grads, void* mc_params,
+                             void* const* flag_ptrs, uint32_t token, int32_t rank, int32_t world, float* exp_avg, float* exp_avg_sq,
+                             int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                             float grad_scale, void* stream);
+
 /* Per-launch CUDA-event timing of the tcgen05 GEMM kernel (the dominant kernel; bench.py's roofline leg).
  * begin() arms it; end() synchronises the device and returns summed kernel milliseconds, FLOPs (2MNK) and
  * launch count since begin(), plus a per-shape text report (with the algorithmic HBM bytes per launch).  While armed,

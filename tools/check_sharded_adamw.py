@@ -1,0 +1,133 @@
+"""torchrun check (N >= 2 GPUs): the fused reduce-scatter + AdamW + all-gather kernel (`NvlinkShardedAdamW`) against
+`dist.all_reduce` + `FlatAdamW` on the same model, batches and seeds; then the time of the exchange + optimiser part alone.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/check_sharded_adamw.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+sys.stdout.flush()
+saved = os.dup(1); os.dup2(2, 1)          # NCCL's banner goes to stderr
+dist.init_process_group("nccl", device_id=dev)
+dist.all_reduce(torch.zeros(1, device=dev)); torch.cuda.synchronize()
+os.dup2(saved, 1); os.close(saved)
+
+import eavqa_b200
+import eavqa_b200.synthetic as syn
+from eavqa_b200.optim import FlatAdamW
+from eavqa_b200.parallel import NvlinkShardedAdamW
+
+W = dict(prefix_length=10, clip_length=10, clip_dim=512, num_layers=8, mapping_type="transformer", model_version="gpt2", vocab=50257)
+lm_cfg = syn.lm_config(W["model_version"], vocab=W["vocab"])
+lm_w = syn.make_lm_weights(lm_cfg, seed=0)
+
+
+def make_model():
+    m = eavqa_b200.ClipCaptionPrefixB200(prefix_length=W["prefix_length"], clip_length=W["clip_length"], prefix_size=W["clip_dim"],
+                                         num_layers=W["num_layers"], mapping_type=W["mapping_type"], model_version=W["model_version"],
+                                         lm_state_dict=lm_w)
+    m.clip_project.load_state_dict(syn.make_mapper_params(W["mapping_type"], W["clip_dim"], lm_cfg["d_model"], W["prefix_length"],
+                                                          W["clip_length"], W["num_layers"], seed=1, perturb_norm=True))
+    return m.to(dev).train()
+
+
+B = 16
+batches = []
+for k in range(3):
+    b = syn.make_caption_batch(B, 40, W["clip_dim"], W["vocab"], seed=100 + 10 * k + rank)
+    batches.append({n: v.to(dev) for n, v in b.items()})
+
+
+def fwd_bwd(model, b):
+    out = model(question_tokens=b["input_ids"], labels=b["labels"], prefix=b["clip_embeddings"], question_mask=b["attention_mask"])
+    out.loss.backward()
+    return out.loss
+
+
+def timed(fn, n=20):
+    for _ in range(3):
+        fn()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+# ---- 1. the exchange + optimiser in isolation: seeded per-rank gradients, three steps, against all-reduce + FlatAdamW.
+#         (Driving both through the training step would compare two runs of a step whose split-K reductions are not
+#         order-deterministic: Adam turns rounding-level gradient noise on near-zero gradients into full-size +-lr updates.)
+ma = make_model()
+oa = FlatAdamW(ma, lr=1e-3)
+p0 = ma._flat.clone()
+n = p0.numel()
+gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+synth = [torch.randn(n, device=dev, generator=gen) * (10.0 ** -(k + 2)) for k in range(3)]
+for g in synth:
+    ga = g.clone()
+    dist.all_reduce(ga)
+    oa.step(ga, grad_scale=1.0 / world)
+torch.cuda.synchronize()
+ref, ref_m, ref_v = ma._flat.clone(), oa.exp_avg.clone(), oa.exp_avg_sq.clone()
+update = (ref - p0).abs().max().item()
+
+results = []
+for multicast, inkernel in ((True, True), (False, True), (True, False)):
+    mb = make_model()
+    ob = NvlinkShardedAdamW(mb, lr=1e-3, use_multicast=multicast, inkernel_barrier=inkernel)
+    for g in synth:
+        ob.grads.copy_(g)
+        ob.step(ob.grads)
+    torch.cuda.synchronize()
+    got = mb._flat
+    diff = (got - ref).abs().max().item()
+    chk = torch.stack([got.double().sum(), got.double().abs().sum()])          # replicas bit-identical?
+    allchk = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allchk, chk)
+    same = all(torch.equal(c, allchk[0]) for c in allchk)
+    sd = ob.state_dict()
+    m_rel = ((sd["exp_avg"] - ref_m).abs().max() / ref_m.abs().max()).item()
+    v_rel = ((sd["exp_avg_sq"] - ref_v).abs().max() / ref_v.abs().max()).item()
+    ok = diff <= 1e-6 * max(1.0, update / 1e-3) and same and m_rel < 1e-6 and v_rel < 1e-6 and not ob.timed_out()
+    results.append(ok)
+    # ---- 2. a training step through it: loss after three optimiser steps
+    for b in batches:
+        loss = fwd_bwd(mb, b)
+        ob.step()
+        ob.zero_grad()
+    t_fused = timed(lambda: ob.step(ob.grads))
+    if rank == 0:
+        print("multicast=%s in-kernel barriers=%s: max |param - reference| = %.3e (largest update %.3e), replicas identical: %s, "
+              "moments rel %.1e / %.1e, timed out: %s, loss after 3 steps %.5f; exchange + AdamW %.3f ms per step" %
+              (ob.multicast, inkernel, diff, update, same, m_rel, v_rel, ob.timed_out(), float(loss), t_fused), flush=True)
+    del ob, mb
+
+for b in batches:
+    loss = fwd_bwd(ma, b)
+    g = ma.last_flat_grads
+    dist.all_reduce(g)
+    oa.step(g, grad_scale=1.0 / world)
+    oa.zero_grad()
+ga = torch.randn_like(ma._flat) * 1e-3
+t_nccl = timed(lambda: (dist.all_reduce(ga), oa.step(ga, grad_scale=1.0 / world)))
+t_ar = timed(lambda: dist.all_reduce(ga))
+if rank == 0:
+    print("NCCL all-reduce + FlatAdamW: loss after 3 steps %.5f; %.3f ms per step (all-reduce alone %.3f ms), %d ranks, %.1f MB of gradients" %
+          (float(loss), t_nccl, t_ar, world, ga.numel() * 4 / 1e6), flush=True)
+ok = all(results)
+if rank == 0:
+    print("CHECK", "PASSED" if ok else "FAILED", flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
