@@ -99,7 +99,12 @@ for multicast, inkernel in ((True, True), (False, True), (True, False)):
     sd = ob.state_dict()
     m_rel = ((sd["exp_avg"] - ref_m).abs().max() / ref_m.abs().max()).item()
     v_rel = ((sd["exp_avg_sq"] - ref_v).abs().max() / ref_v.abs().max()).item()
-    ok = diff <= 1e-6 * max(1.0, update / 1e-3) and same and m_rel < 1e-6 and v_rel < 1e-6 and not ob.timed_out()
+    # the switch's reduction and NCCL's NVLS all-reduce add in the same order, and two addends commute: bit-exact there.  Peer
+    # loads summed in rank order differ from NCCL's order in the last bit of the gradient sum (moments to ~2e-7); Adam turns
+    # that into up to a few percent of one update where the summed gradient nearly cancels.
+    exact = ob.multicast or world <= 2
+    ok = (diff == 0.0 and m_rel == 0.0 and v_rel == 0.0) if exact else (diff <= 0.05 * update and m_rel < 1e-6 and v_rel < 1e-6)
+    ok = ok and same and not ob.timed_out()
     results.append(ok)
     # ---- 2. a training step through it: loss after three optimiser steps
     for b in batches:
