@@ -205,9 +205,10 @@ def main():
     ap.add_argument("--only-timed", action="store_true", help="run only warm-up + the timed region (for ncu launch lists)")
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="N > 1: bucketed gradient all-reduce overlapped with the mapper backward instead of one all-reduce after the step")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+    ap.add_argument("--exchange", default="fused", choices=["fused", "fused-overlap", "nccl"],
                     help="N > 1: 'fused' = ONE kernel per rank does reduce-scatter + AdamW + all-gather over NVLink peer / multicast "
-                         "memory (eavqa_sharded_adamw_step); 'nccl' = NCCL all-reduce of the flat gradient, then the fused AdamW on every rank")
+                         "memory (eavqa_sharded_adamw_step); 'fused-overlap' = the same kernel per gradient bucket on a communication "
+                         "stream while the mapper backward still runs; 'nccl' = NCCL all-reduce of the flat gradient, then the fused AdamW on every rank")
     ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: cap on NCCL's CTAs per collective (0 = NCCL's default)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the headline): 256 samples per GPU; strong: 256 samples in total, 256 / N per GPU (SURVEY.md 8d)")
@@ -276,14 +277,15 @@ def main():
     from eavqa_b200.parallel import NvlinkShardedAdamW, OverlappedGradReducer
     global ALLREDUCE_NOTE
     opt, fused = None, False
-    if world > 1 and args.exchange == "fused" and not args.overlap_allreduce:
+    if world > 1 and args.exchange.startswith("fused") and not args.overlap_allreduce:
         # the exchange step and the optimiser as ONE kernel per rank over NVLink / NVSwitch peer memory (csrc/collective.cu).
         # Measured (profiles/README.md, round 2): N = 2 0.277 ms against 0.535 ms for NCCL all-reduce + AdamW.
         try:
-            opt = NvlinkShardedAdamW(model, lr=1e-4)
+            opt = NvlinkShardedAdamW(model, lr=1e-4, overlap=args.exchange == "fused-overlap")
             fused = True
-            ALLREDUCE_NOTE = ("none: reduce-scatter + AdamW + all-gather fused in one kernel per rank (%s), barriers inside the kernel"
-                              % ("NVLS multimem.ld_reduce / multimem.st" if opt.multicast else "NVLink peer loads / stores"))
+            ALLREDUCE_NOTE = ("none: reduce-scatter + AdamW + all-gather fused in one kernel per rank (%s), barriers inside the kernel%s"
+                              % ("NVLS multimem.ld_reduce / multimem.st" if opt.multicast else "NVLink peer loads / stores",
+                                 "; per gradient bucket on a communication stream during the mapper backward" if opt.overlap else ""))
         except Exception as e:      # symmetric memory unavailable on this box: the NCCL path below, and the line says so
             print("[bench] fused exchange unavailable (%s: %s); using the NCCL all-reduce" % (type(e).__name__, e), file=sys.stderr)
             opt = None

@@ -340,11 +340,11 @@ int eavqa_sharded_adamw_range(int64_t n, int32_t rank, int32_t world, int64_t* b
 
 int eavqa_sharded_adamw_step(void* const* grad_ptrs, void* const* param_ptrs, const void* mc_grads, void* mc_params,
                              void* const* flag_ptrs, uint32_t token, int32_t rank, int32_t world, float* exp_avg, float* exp_avg_sq,
-                             int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                             float grad_scale, void* stream) {
+                             int64_t offset, int64_t n, int32_t max_ctas, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int32_t step, float grad_scale, void* stream) {
     API_BEGIN
-    sharded_adamw_step(grad_ptrs, param_ptrs, mc_grads, mc_params, flag_ptrs, token, rank, world, exp_avg, exp_avg_sq, n, lr, beta1,
-                       beta2, eps, weight_decay, step, grad_scale, S(stream));
+    sharded_adamw_step(grad_ptrs, param_ptrs, mc_grads, mc_params, flag_ptrs, token, rank, world, exp_avg, exp_avg_sq, offset, n,
+                       max_ctas, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
     API_END
 }
 

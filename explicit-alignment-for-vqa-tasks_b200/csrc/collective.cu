@@ -167,10 +167,11 @@ void sharded_adamw_range(int64_t n, int rank, int world, int64_t* begin, int64_t
 }
 
 void sharded_adamw_step(void* const* grad_ptrs, void* const* param_ptrs, const void* mc_grads, void* mc_params, void* const* flag_ptrs,
-                        uint32_t token, int rank, int world, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                        float eps, float weight_decay, int step, float grad_scale, cudaStream_t s) {
+                        uint32_t token, int rank, int world, float* m, float* v, int64_t offset, int64_t n, int max_ctas, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t s) {
     EAVQA_CHECK(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "sharded_adamw_step: rank / world");
-    EAVQA_CHECK(n % 4 == 0 && step >= 1, "sharded_adamw_step: n must be a multiple of 4 and step >= 1");
+    EAVQA_CHECK(n % 4 == 0 && offset % 4 == 0 && offset >= 0 && step >= 1 && max_ctas >= 0,
+                "sharded_adamw_step: offset and n must be multiples of 4 and step >= 1");
     EAVQA_CHECK(grad_ptrs != nullptr && param_ptrs != nullptr && m != nullptr && v != nullptr, "sharded_adamw_step: null argument");
     EAVQA_CHECK((mc_grads == nullptr) == (mc_params == nullptr), "sharded_adamw_step: both multicast addresses or neither");
     PeerPtrs g = {}, p = {}, f = {};
@@ -183,8 +184,12 @@ void sharded_adamw_step(void* const* grad_ptrs, void* const* param_ptrs, const v
             f.p[r] = flag_ptrs[r];
         }
     }
+    // the range [offset, offset + n) of the flat buffers is what this call exchanges (the whole buffer, or one gradient bucket
+    // while the rest of the backward still runs); rank r owns its r-th shard
     int64_t begin = 0, end = 0;
     sharded_adamw_range(n, rank, world, &begin, &end);
+    begin += offset;
+    end += offset;
     const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
     const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
     // every CTA must be resident while it spins in the start barrier: one CTA per SM at most.
@@ -193,7 +198,7 @@ void sharded_adamw_step(void* const* grad_ptrs, void* const* param_ptrs, const v
     if (const char* cfg = getenv("EAVQA_SHARD_CFG")) sscanf(cfg, "%d,%d", &threads, &unroll);
     EAVQA_CHECK(threads >= 64 && threads <= 1024 && threads % 32 == 0 && (unroll == 2 || unroll == 4 || unroll == 8), "EAVQA_SHARD_CFG");
     const int64_t work4 = std::max<int64_t>((end - begin) / 4, 1);
-    const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(work4, threads), num_sms()));
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(work4, threads), max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms()));
     const bool mc = mc_grads != nullptr;
 #define EAVQA_SHARD_LAUNCH(MC_, U_)                                                                                            \
     launch_kernel(sharded_adamw_kernel<MC_, U_>, dim3(grid), dim3(threads), 0, s, g, p, static_cast<const float4*>(mc_grads),   \

@@ -123,10 +123,11 @@ void sharded_adamw_range(int64_t n, int rank, int world, int64_t* begin, int64_t
 // ONE kernel: sum of all ranks' gradients for this rank's shard (NVLS multicast load-reduce, or peer loads in rank order),
 // AdamW on the shard, updated parameters stored to every rank (multicast store, or peer stores).  grad_ptrs / param_ptrs /
 // flag_ptrs: rank r's buffer as mapped into THIS process (symmetric memory); mc_*: multicast addresses or null; flag_ptrs
-// null = no barriers inside the kernel (the caller brackets the call with its own cross-GPU barriers).
+// null = no barriers inside the kernel (the caller brackets the call with its own cross-GPU barriers).  The call exchanges
+// elements [offset, offset + n) of the buffers (sharded over the ranks) on at most max_ctas CTAs (0 = one per SM).
 void sharded_adamw_step(void* const* grad_ptrs, void* const* param_ptrs, const void* mc_grads, void* mc_params, void* const* flag_ptrs,
-                        uint32_t token, int rank, int world, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                        float eps, float weight_decay, int step, float grad_scale, cudaStream_t s);
+                        uint32_t token, int rank, int world, float* m, float* v, int64_t offset, int64_t n, int max_ctas, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t s);
 
 // ---------------------------------------------------------------- attention (attention.cu)
 // GPT-2 causal attention with key-padding mask, head_dim 64, qkv [B*T, 3d] bf16 (q | k | v, heads contiguous).

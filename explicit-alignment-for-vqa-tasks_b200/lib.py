@@ -60,8 +60,8 @@ PROTOTYPES = {
                                    C.c_float, c_int32, C.c_float, c_void_p]),
     "eavqa_sharded_adamw_range": (C.c_int, [c_int64, c_int32, c_int32, C.POINTER(c_int64), C.POINTER(c_int64)]),
     "eavqa_sharded_adamw_step": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_uint32, c_int32, c_int32, c_void_p,
-                                           c_void_p, c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_int32,
-                                           C.c_float, c_void_p]),
+                                           c_void_p, c_int64, c_int64, c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                           c_int32, C.c_float, c_void_p]),
     "eavqa_profile_begin": (C.c_int, []),
     "eavqa_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_int64), c_char_p, c_size_t]),
     "eavqa_op_gemm": (C.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32,

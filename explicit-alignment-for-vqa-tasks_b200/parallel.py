@@ -161,10 +161,18 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
 
     Use: ``opt = NvlinkShardedAdamW(model)`` after ``dist.init_process_group("nccl")``; then per step ``loss.backward()``,
     ``opt.step()``, ``opt.zero_grad()``.  ``p.grad`` holds the LOCAL (un-reduced) gradient in this mode.
+
+    ``overlap=True``: the buffer is exchanged bucket by bucket (the engine's gradient buckets: pairs of mapper layers, final
+    long before the mapper backward ends; ``eavqa_set_grad_events``) on a communication stream, each call on at most
+    ``overlap_ctas`` CTAs -- the kernel is bound by NVLink, not by SMs -- while the backward still running keeps the other
+    SMs; only the last bucket and the ranges no bucket covers are exchanged after the step.  A bucket's parameters are
+    rewritten while the backward of the layers below still runs: safe, because a bucket's start barrier waits until EVERY rank
+    has finished the backward of those layers, after which no rank reads them again in this step.  Use with a plain
+    ``loss.backward()`` (upstream gradient 1), as for ``OverlappedGradReducer``.
     """
 
     def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, group=None,
-                 use_multicast: Optional[bool] = None, inkernel_barrier: bool = True):
+                 use_multicast: Optional[bool] = None, inkernel_barrier: bool = True, overlap: bool = False, overlap_ctas: int = 24):
         import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
         from . import lib as _lib
@@ -213,6 +221,33 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
         self._mc_g = C.c_void_p(mc_g + g_off) if self.multicast else None
         self._mc_p = C.c_void_p(mc_p + p_off) if self.multicast else None
         self._lib = _lib
+        self.overlap = bool(overlap and inkernel_barrier)
+        self.overlap_ctas = int(overlap_ctas)
+        self._events, self._buckets, self._rest = [], [], [(0, n)]
+        if self.overlap:
+            L = _lib.load()
+            h = model._handle
+            ranges = []
+            for i in range(L.eavqa_grad_bucket_count(h)):
+                b, e = C.c_int64(), C.c_int64()
+                _lib.check(L.eavqa_grad_bucket_range(h, i, C.byref(b), C.byref(e)))
+                ranges.append((b.value, e.value))
+            self._buckets, self._rest = bucket_plan(n, ranges)
+            if any(b % 4 or e % 4 for b, e in self._buckets + self._rest):
+                raise ValueError("gradient bucket boundaries must be multiples of 4 floats")
+            self._events = [torch.cuda.Event(enable_timing=False) for _ in self._buckets]
+            for ev in self._events:
+                ev.record()                               # materialises the cudaEvent_t the engine will re-record
+            self._comm = torch.cuda.Stream(device=dev)
+            if self._events:
+                arr = (C.c_void_p * len(self._events))(*[C.c_void_p(ev.cuda_event) for ev in self._events])
+                _lib.check(L.eavqa_set_grad_events(h, arr, len(self._events)))
+        # what this rank owns: its shard of every range one call exchanges
+        self.owned = []
+        for (b, e) in (self._buckets + self._rest if self.overlap else [(0, n)]):
+            sb, se = shard_range(e - b, self.rank, self.world)
+            if se > sb:
+                self.owned.append((b + sb, b + se))
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)                         # every rank's flags are zero before the first kernel signals
 
@@ -225,7 +260,8 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
         full = []
         for t in (self.exp_avg, self.exp_avg_sq):
             f = torch.zeros_like(t)
-            f[self.begin:self.end] = t[self.begin:self.end]
+            for b, e in self.owned:
+                f[b:e] = t[b:e]
             dist.all_reduce(f, group=self.group)
             full.append(f)
         return {"steps": self.steps, "exp_avg": full[0], "exp_avg_sq": full[1],
@@ -249,17 +285,46 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
                                "(the module was moved or re-flattened after the optimiser was built)")
         grp = self.param_groups[0]
         self.steps += 1
-        self._token = (self._token + 1) & 0xffffffff
-        with torch.cuda.device(self.params.device):
-            if not self.inkernel_barrier:
-                self._h_grads.barrier(channel=0)
-            self._lib.check(self._lib.load().eavqa_sharded_adamw_step(
+        L = self._lib.load()
+
+        def launch(offset, count, max_ctas, stream):
+            self._token = (self._token + 1) & 0xffffffff
+            self._lib.check(L.eavqa_sharded_adamw_step(
                 self._g_ptrs, self._p_ptrs, self._mc_g, self._mc_p, self._f_ptrs if self.inkernel_barrier else None,
-                self._token, self.rank, self.world, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.n,
+                self._token, self.rank, self.world, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), offset, count, max_ctas,
                 float(grp["lr"]), grp["betas"][0], grp["betas"][1], grp["eps"], grp["weight_decay"], self.steps,
-                1.0 / self.world, self._lib.current_stream()))
+                1.0 / self.world, stream))
+
+        with torch.cuda.device(self.params.device):
+            cur = torch.cuda.current_stream(self.params.device)
+            if self.overlap:
+                # every bucket but the last: on the communication stream as soon as its gradients are final, on a few CTAs
+                with torch.cuda.stream(self._comm):
+                    for (b, e), ev in list(zip(self._buckets, self._events))[:-1]:
+                        self._comm.wait_event(ev)
+                        launch(b, e - b, self.overlap_ctas, self._comm.cuda_stream)
+                    self._comm.wait_stream(cur)           # the backward is complete: the rest at full width
+                    for (b, e) in self._buckets[-1:] + self._rest:
+                        launch(b, e - b, 0, self._comm.cuda_stream)
+                cur.wait_stream(self._comm)
+                return
             if not self.inkernel_barrier:
                 self._h_grads.barrier(channel=0)
+            launch(0, self.n, 0, self._lib.current_stream())
+            if not self.inkernel_barrier:
+                self._h_grads.barrier(channel=0)
+
+    def close(self):
+        """Uninstall the bucket events from the engine (it only borrows them)."""
+        if self._events and self.model._handle is not None:
+            self._lib.check(self._lib.load().eavqa_set_grad_events(self.model._handle, None, 0))
+        self._events = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def timed_out(self) -> bool:
         """True when a barrier spin inside the kernel gave up after 10 s (a peer never made the call)."""

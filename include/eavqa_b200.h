@@ -177,13 +177,17 @@ int eavqa_adamw_step(float* params, const float* grads, float* exp_avg, float* e
  * this process (symmetric-memory allocations of the host side); flag_ptrs: 64 zero-initialised uint32 per rank used by the
  * two barriers inside the kernel (all gradients final / all stores landed), `token` must grow by one per call, starting at 1;
  * flag_ptrs == NULL: no barriers inside (the caller brackets the call with its own cross-GPU barriers).
- * Every rank must make the call, on a stream ordered after its backward; the kernel completes only after all ranks' stores
- * into this rank's parameters have landed.  n % 4 == 0, world <= 16. */
+ * One call exchanges elements [offset, offset + n) of the buffers, sharded over the ranks by eavqa_sharded_adamw_range(n, ...)
+ * + offset: the whole flat buffer after the step, or one gradient bucket (eavqa_grad_bucket_range) on a communication stream
+ * as soon as its event (eavqa_set_grad_events) fires, on at most max_ctas CTAs (0 = one per SM) so that the backward still
+ * running keeps its SMs.  Every rank must make the same sequence of calls, each on a stream ordered after the gradients of
+ * its range; a call completes only after all ranks' stores into this rank's parameters have landed.  offset, n % 4 == 0,
+ * world <= 16. */
 int eavqa_sharded_adamw_range(int64_t n, int32_t rank, int32_t world, int64_t* begin, int64_t* end);
 int eavqa_sharded_adamw_step(void* const* grad_ptrs, void* const* param_ptrs, const void* mc_grads, void* mc_params,
                              void* const* flag_ptrs, uint32_t token, int32_t rank, int32_t world, float* exp_avg, float* exp_avg_sq,
-                             int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                             float grad_scale, void* stream);
+                             int64_t offset, int64_t n, int32_t max_ctas, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int32_t step, float grad_scale, void* stream);
 
 /* Per-launch CUDA-event timing of the tcgen05 GEMM kernel (the dominant kernel; bench.py's roofline leg).
  * begin() arms it; end() synchronises the device and returns summed kernel milliseconds, FLOPs (2MNK) and

@@ -107,8 +107,11 @@ def _ptr_array(tensors):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,n,inkernel", [(1, 4096, False), (1, 4096, True), (2, 40_000, True), (4, 100_004, True), (2, 8, True)])
-def test_sharded_adamw_simulated_ranks_on_one_device(world, n, inkernel):
+@pytest.mark.parametrize("world,n,inkernel,ranges", [(1, 4096, False, None), (1, 4096, True, None), (2, 40_000, True, None),
+                                                    (4, 100_004, True, None), (2, 8, True, None),
+                                                    (2, 40_000, True, [(30_000, 10_000), (8_000, 22_000), (0, 8_000)]),
+                                                    (3, 20_008, True, [(20_000, 8), (4, 19_996), (0, 4)])])
+def test_sharded_adamw_simulated_ranks_on_one_device(world, n, inkernel, ranges):
     L = L_.load()
     dev = "cuda"
     torch.manual_seed(3)
@@ -131,9 +134,15 @@ def test_sharded_adamw_simulated_ranks_on_one_device(world, n, inkernel):
         torch.cuda.synchronize()
         for r in range(world):
             with torch.cuda.stream(streams[r]):
-                L_.check(L.eavqa_sharded_adamw_step(gp, pp, None, None, fp if inkernel else None, step, r, world, m[r].data_ptr(),
-                                                    v[r].data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 1.0 / world,
-                                                    streams[r].cuda_stream))
+                if ranges is None:
+                    L_.check(L.eavqa_sharded_adamw_step(gp, pp, None, None, fp if inkernel else None, step, r, world, m[r].data_ptr(),
+                                                        v[r].data_ptr(), 0, n, 0, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 1.0 / world,
+                                                        streams[r].cuda_stream))
+                else:       # the buffer exchanged range by range (gradient buckets), a few CTAs each, one barrier generation per call
+                    for k, (off, cnt) in enumerate(ranges):
+                        L_.check(L.eavqa_sharded_adamw_step(gp, pp, None, None, fp, (step - 1) * len(ranges) + k + 1, r, world,
+                                                            m[r].data_ptr(), v[r].data_ptr(), off, cnt, 2, 1e-3, 0.9, 0.999, 1e-8, 0.01,
+                                                            step, 1.0 / world, streams[r].cuda_stream))
         torch.cuda.synchronize()
         # the library's own fused AdamW on the summed gradient (bit-exact: same arithmetic, same order)
         L_.check(L.eavqa_adamw_step(ref_p.data_ptr(), total.data_ptr(), ref_m.data_ptr(), ref_v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8,
@@ -147,11 +156,12 @@ def test_sharded_adamw_simulated_ranks_on_one_device(world, n, inkernel):
     # torch.optim.AdamW: what the reference's executor builds
     assert (params[0] - tp.detach()).abs().max().item() <= 2e-6
     for r in range(world):
-        b, e = shard_range(n, r, world)
-        assert torch.equal(m[r][b:e], ref_m[b:e]) and torch.equal(v[r][b:e], ref_v[b:e])
-        outside = torch.ones(n, dtype=torch.bool, device=dev)
-        outside[b:e] = False
-        assert float(m[r][outside].abs().sum()) == 0.0          # only the own shard of the moments is touched
+        own = torch.zeros(n, dtype=torch.bool, device=dev)
+        for off, cnt in (ranges if ranges is not None else [(0, n)]):
+            b, e = shard_range(cnt, r, world)
+            own[off + b:off + e] = True
+        assert torch.equal(m[r][own], ref_m[own]) and torch.equal(v[r][own], ref_v[own])
+        assert float(m[r][~own].abs().sum()) == 0.0             # only the own shards of the moments are touched
 
 
 @pytest.mark.gpu
@@ -160,7 +170,7 @@ def test_sharded_adamw_rejects_bad_arguments():
     t = torch.zeros(8, device="cuda")
     arr = _ptr_array([t])
     s = torch.cuda.current_stream().cuda_stream
-    assert L.eavqa_sharded_adamw_step(arr, arr, None, None, None, 1, 0, 1, t.data_ptr(), t.data_ptr(), 6, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0, s) != 0
-    assert L.eavqa_sharded_adamw_step(arr, arr, None, None, None, 1, 1, 1, t.data_ptr(), t.data_ptr(), 8, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0, s) != 0
-    assert L.eavqa_sharded_adamw_step(arr, arr, t.data_ptr(), None, None, 1, 0, 1, t.data_ptr(), t.data_ptr(), 8, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0, s) != 0
+    assert L.eavqa_sharded_adamw_step(arr, arr, None, None, None, 1, 0, 1, t.data_ptr(), t.data_ptr(), 0, 6, 0, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0, s) != 0
+    assert L.eavqa_sharded_adamw_step(arr, arr, None, None, None, 1, 1, 1, t.data_ptr(), t.data_ptr(), 0, 8, 0, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0, s) != 0
+    assert L.eavqa_sharded_adamw_step(arr, arr, t.data_ptr(), None, None, 1, 0, 1, t.data_ptr(), t.data_ptr(), 0, 8, 0, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 1.0, s) != 0
     assert b"sharded_adamw_step" in L.eavqa_last_error()
