@@ -188,7 +188,14 @@ Engine::Engine(const eavqa_config& cfg) : cfg_(cfg) {
     for (auto& l : layers_) std::memset(&l, 0, sizeof(LmLayer));
     const char* e = getenv("EAVQA_WGRAD_STREAM");
     side_enabled_ = !(e != nullptr && e[0] == '0');
-    CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    {
+        // EAVQA_WGRAD_PRIO=high: the side stream of the mapper's weight-gradient GEMMs above the caller's stream (A/B knob)
+        const char* pr = getenv("EAVQA_WGRAD_PRIO");
+        int least = 0, greatest = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        const int prio = (pr != nullptr && pr[0] == 'h') ? greatest : least;
+        CUDA_CHECK(cudaStreamCreateWithPriority(&side_, cudaStreamNonBlocking, prio));
+    }
     CUDA_CHECK(cudaEventCreateWithFlags(&join_event_, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&bucket_sync_event_, cudaEventDisableTiming));
 }
