@@ -526,6 +526,62 @@ def test_overlapped_grad_reducer_on_a_one_rank_nccl_group():
         dist.destroy_process_group()
 
 
+def test_nvlink_sharded_adamw_on_a_one_rank_nccl_group():
+    """``parallel.NvlinkShardedAdamW`` (symmetric-memory buffers, the fused exchange + AdamW kernel with its barriers, and
+    the per-bucket mode driven by the engine's events) on a world of one: the module's parameters and gradients move into
+    symmetric memory without changing the step, and three optimiser steps equal ``FlatAdamW`` on the same gradients.
+    (N = 2 / 4 / 8, peer and multicast paths: tools/check_sharded_adamw.py under torchrun.)"""
+    import socket
+    import torch.distributed as dist
+    from eavqa_b200.optim import FlatAdamW
+    from eavqa_b200.parallel import NvlinkShardedAdamW
+    case = CASES["train_tiny_transformer"]
+    lm_w, mapper_w, batch, cfg = build_case(case)
+    kw = dict(question_tokens=batch["input_ids"], labels=batch["labels"], prefix=batch["clip_embeddings"],
+              question_mask=batch["attention_mask"])
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, world_size=1, rank=0, device_id=torch.device("cuda", 0))
+    try:
+        for overlap in (False, True):
+            ref_model = build_model(case, lm_w, mapper_w)
+            ref_opt = FlatAdamW(ref_model, lr=1e-3)
+            model = build_model(case, lm_w, mapper_w)
+            loss0 = float(model(**kw).loss)
+            try:
+                opt = NvlinkShardedAdamW(model, lr=1e-3, overlap=overlap)
+            except RuntimeError as e:       # no symmetric memory on this box / driver
+                pytest.skip("symmetric memory unavailable: %s" % e)
+            assert opt.overlap == overlap and model._flat is opt.params
+            assert all(p.data_ptr() == opt.params.data_ptr() + 4 * o for p, (o, _, _) in zip(model._param_list, model._slices))
+            assert abs(float(model(**kw).loss) - loss0) <= 1e-6 * abs(loss0)       # re-homing the parameters changed nothing
+            spans = sorted(opt.owned)
+            assert spans[0][0] == 0 and spans[-1][1] == opt.n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            for step in range(3):
+                model(**kw).loss.backward()
+                assert model.last_flat_grads.data_ptr() == opt.grads.data_ptr()      # the backward wrote into symmetric memory
+                g = model.last_flat_grads.clone()
+                assert all(p.grad is not None for p in model.clip_project.parameters())
+                opt.step()
+                opt.zero_grad()
+                ref_opt.step(g)              # the same gradient through the plain fused AdamW
+                torch.cuda.synchronize()
+                assert not opt.timed_out()
+                assert torch.equal(model._flat, ref_model._flat), "overlap=%s step %d" % (overlap, step)
+            sd = opt.state_dict()
+            assert torch.equal(sd["exp_avg"], ref_opt.exp_avg) and torch.equal(sd["exp_avg_sq"], ref_opt.exp_avg_sq) and sd["steps"] == 3
+            assert float(model(**kw).loss) < loss0                                   # and it trains
+            opt.close()
+            model = model.cpu().cuda()          # re-flattened: the symmetric buffers are no longer the module's own
+            model(**kw).loss.backward()
+            with pytest.raises(RuntimeError):
+                opt.step()
+    finally:
+        dist.destroy_process_group()
+
+
 def test_decode_attention_long_history_crosses_the_staging_limit():
     """Greedy decoding whose KV history grows from 218 to 231 keys: the first steps use the decode-attention kernel that
     stages the whole history in shared memory (<= 224 keys), the later ones the direct-load kernel.  Tiny sharpened LM,
