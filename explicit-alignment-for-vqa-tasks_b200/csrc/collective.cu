@@ -86,7 +86,7 @@ __device__ __forceinline__ void adamw_update(float4& pp, const float4& gg, float
 
 // MC: gradients / parameters through the NVLS multicast mapping; otherwise through per-rank peer pointers.
 template <bool MC, int U>
-__global__ void __launch_bounds__(1024, 1) sharded_adamw_kernel(const __grid_constant__ PeerPtrs grads, const __grid_constant__ PeerPtrs params,
+__global__ void __launch_bounds__(512, 1) sharded_adamw_kernel(const __grid_constant__ PeerPtrs grads, const __grid_constant__ PeerPtrs params,
                                                             const float4* __restrict__ mc_grads, float4* __restrict__ mc_params,
                                                             float4* __restrict__ m, float4* __restrict__ v,
                                                             const __grid_constant__ PeerPtrs flags, uint32_t token,
@@ -107,7 +107,18 @@ __global__ void __launch_bounds__(1024, 1) sharded_adamw_kernel(const __grid_con
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     // U gradient loads in flight per thread: NVLink round trips are several microseconds
     for (int64_t i0 = begin4 + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i0 < end4; i0 += U * stride) {
-        float4 gg[U];
+        float4 gg[U], pp[U], mm[U], vv[U];
+        // every load of the iteration is issued before the first result is needed: the local parameter / moment loads travel
+        // with the gradient loads instead of starting when those arrive (round-2 SASS: LDGMC x4, wait, then LDG per element)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < end4) {
+                pp[u] = my_params[i];
+                mm[u] = m[i];
+                vv[u] = v[i];
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t i = i0 + u * stride;
@@ -128,14 +139,13 @@ __global__ void __launch_bounds__(1024, 1) sharded_adamw_kernel(const __grid_con
         for (int u = 0; u < U; ++u) {
             const int64_t i = i0 + u * stride;
             if (i < end4) {
-                float4 pp = my_params[i], mm = m[i], vv = v[i];
-                adamw_update(pp, gg[u], mm, vv, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, gscale);
-                m[i] = mm;
-                v[i] = vv;
+                adamw_update(pp[u], gg[u], mm[u], vv[u], lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, gscale);
+                m[i] = mm[u];
+                v[i] = vv[u];
                 if (MC) {
-                    multimem_st(mc_params + i, pp);
+                    multimem_st(mc_params + i, pp[u]);
                 } else {
-                    for (int r = 0; r < world; ++r) static_cast<float4*>(params.p[r])[i] = pp;
+                    for (int r = 0; r < world; ++r) static_cast<float4*>(params.p[r])[i] = pp[u];
                 }
             }
         }
@@ -193,10 +203,10 @@ void sharded_adamw_step(void* const* grad_ptrs, void* const* param_ptrs, const v
     const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
     const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
     // every CTA must be resident while it spins in the start barrier: one CTA per SM at most.
-    // EAVQA_SHARD_CFG="threads,U" (tuning knob): threads per CTA (<= 1024), gradient loads in flight per thread (2 / 4 / 8)
+    // EAVQA_SHARD_CFG="threads,U" (tuning knob): threads per CTA (<= 512), gradient loads in flight per thread (2 / 4 / 8)
     int threads = 512, unroll = 4;
     if (const char* cfg = getenv("EAVQA_SHARD_CFG")) sscanf(cfg, "%d,%d", &threads, &unroll);
-    EAVQA_CHECK(threads >= 64 && threads <= 1024 && threads % 32 == 0 && (unroll == 2 || unroll == 4 || unroll == 8), "EAVQA_SHARD_CFG");
+    EAVQA_CHECK(threads >= 64 && threads <= 512 && threads % 32 == 0 && (unroll == 2 || unroll == 4 || unroll == 8), "EAVQA_SHARD_CFG");
     const int64_t work4 = std::max<int64_t>((end - begin) / 4, 1);
     const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(work4, threads), max_ctas > 0 ? std::min(max_ctas, num_sms()) : num_sms()));
     const bool mc = mc_grads != nullptr;
