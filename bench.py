@@ -382,6 +382,19 @@ def main():
     e2e = {"value": B * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
            "ms_per_step": ms_e2e}
 
+    # ---- N > 1: the exchange step + optimiser on its own (gradients already final), against the NVLink bytes it moves ------
+    exchange = None
+    if fused:
+        for _ in range(3):
+            opt.step(opt.grads)
+        ms_x = timed(lambda: opt.step(opt.grads), 10)
+        gb = opt.link_bytes_per_direction() / 1e9
+        exchange = {"kernel": "sharded_adamw_kernel (reduce-scatter + AdamW + all-gather, one launch per rank)", "ms": ms_x,
+                    "path": "NVLS multimem.ld_reduce / multimem.st" if opt.multicast else "NVLink peer loads / stores",
+                    "link_gbytes_per_direction": gb, "achieved_gb_s_per_direction": gb / (ms_x * 1e-3),
+                    "nominal_peak_gb_s_per_direction": 900.0,
+                    "note": "timed alone with CUDA events, max over ranks; bytes per GPU and direction (parallel.NvlinkShardedAdamW.link_bytes_per_direction)"}
+
     # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events, outside the timed region --------------
     import ctypes as C
     pk = peaks()
@@ -426,6 +439,8 @@ def main():
             "dtype": "bf16", "data": "synthetic", "config": dict(workload_config(world), batch_per_gpu=B, global_batch=B * world),
             "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "loss_check": loss_check}
+    if exchange is not None:
+        line["exchange"] = exchange
 
     # ---- few-shot VQA answers/s (BASELINE configs[3]) and the CPU baseline: rank 0, N = 1 only ------------------------
     if reducer is not None:

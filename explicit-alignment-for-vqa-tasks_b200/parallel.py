@@ -147,6 +147,17 @@ def shard_range(n: int, rank_: int, world_: int):
     return min(n4, per * rank_) * 4, min(n4, per * (rank_ + 1)) * 4
 
 
+def owned_ranges(ranges, rank_: int, world_: int):
+    """What ``rank_`` owns when a flat buffer is exchanged range by range (one ``eavqa_sharded_adamw_step`` call per
+    ``(begin, end)`` in ``ranges``): its shard of every range.  Over all ranks these tile the union of ``ranges``."""
+    out = []
+    for b, e in ranges:
+        sb, se = shard_range(e - b, rank_, world_)
+        if se > sb:
+            out.append((b + sb, b + se))
+    return out
+
+
 class NvlinkShardedAdamW(torch.optim.Optimizer):
     """The data-parallel exchange step and the optimiser as ONE kernel per rank (reduce-scatter + AdamW + all-gather).
 
@@ -243,11 +254,7 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
                 arr = (C.c_void_p * len(self._events))(*[C.c_void_p(ev.cuda_event) for ev in self._events])
                 _lib.check(L.eavqa_set_grad_events(h, arr, len(self._events)))
         # what this rank owns: its shard of every range one call exchanges
-        self.owned = []
-        for (b, e) in (self._buckets + self._rest if self.overlap else [(0, n)]):
-            sb, se = shard_range(e - b, self.rank, self.world)
-            if se > sb:
-                self.owned.append((b + sb, b + se))
+        self.owned = owned_ranges(self._buckets + self._rest if self.overlap else [(0, n)], self.rank, self.world)
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)                         # every rank's flags are zero before the first kernel signals
 
@@ -325,6 +332,15 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
             self.close()
         except Exception:
             pass
+
+    def link_bytes_per_direction(self) -> int:
+        """Bytes one step's exchange moves over this GPU's NVLink ports in EACH direction: through the multicast mapping the
+        gradient buffer once out (a rank's own copy travels to the switch too) plus its shard of the parameters, and the
+        mirror image in; through peer pointers (W - 1) / W of the buffer for the gradients plus as much for the parameters."""
+        nbytes = 4 * self.n
+        if self.multicast:
+            return nbytes + nbytes // self.world
+        return 2 * nbytes * (self.world - 1) // self.world
 
     def timed_out(self) -> bool:
         """True when a barrier spin inside the kernel gave up after 10 s (a peer never made the call)."""

@@ -18,7 +18,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from eavqa_b200 import lib as L_
-from eavqa_b200.parallel import shard_range
+from eavqa_b200.parallel import bucket_plan, owned_ranges, shard_range
 
 
 def test_shard_range_matches_the_c_abi_and_tiles_the_buffer():
@@ -37,6 +37,22 @@ def test_shard_range_matches_the_c_abi_and_tiles_the_buffer():
         shard_range(6, 0, 2)
     with pytest.raises(ValueError):
         shard_range(8, 2, 2)
+
+
+def test_owned_ranges_tile_the_buffer_bucket_by_bucket():
+    """Per-bucket exchange: every rank owns its shard of every bucket; over the ranks these tile the whole flat buffer."""
+    n = 4 * 1000
+    buckets, rest = bucket_plan(n, [(2400, 3600), (1200, 2400), (400, 1200)])     # completion order; [0, 400) and [3600, n) uncovered
+    assert rest == [(0, 400), (3600, 4000)]
+    for world in (1, 2, 3, 8):
+        cover = []
+        for r in range(world):
+            mine = owned_ranges(buckets + rest, r, world)
+            assert all(b % 4 == 0 and e % 4 == 0 and e > b for b, e in mine)
+            cover += mine
+        cover.sort()
+        assert cover[0][0] == 0 and cover[-1][1] == n and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+    assert owned_ranges([(0, 8)], 3, 4) == []          # 2 float4 over 4 ranks: the last ranks own nothing
 
 
 def _free_port():
