@@ -388,6 +388,7 @@ def main():
         for _ in range(3):
             opt.step(opt.grads)
         ms_x = timed(lambda: opt.step(opt.grads), 10)
+        assert not opt.timed_out(), "bench.py: a barrier inside the fused exchange kernel timed out (a rank fell out of step)"
         gb = opt.link_bytes_per_direction() / 1e9
         exchange = {"kernel": "sharded_adamw_kernel (reduce-scatter + AdamW + all-gather, one launch per rank)", "ms": ms_x,
                     "path": "NVLS multimem.ld_reduce / multimem.st" if opt.multicast else "NVLink peer loads / stores",

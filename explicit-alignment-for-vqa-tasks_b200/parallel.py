@@ -171,7 +171,10 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
     in); each element is computed by exactly one rank, so all replicas stay bit-identical.
 
     Use: ``opt = NvlinkShardedAdamW(model)`` after ``dist.init_process_group("nccl")``; then per step ``loss.backward()``,
-    ``opt.step()``, ``opt.zero_grad()``.  ``p.grad`` holds the LOCAL (un-reduced) gradient in this mode.
+    ``opt.step()``, ``opt.zero_grad()``.  ``p.grad`` holds the LOCAL (un-reduced) gradient in this mode.  One backward per
+    step: every backward overwrites the symmetric gradient buffer, so gradient accumulation over micro-batches needs
+    ``FlatAdamW`` (``accumulate()``) with an NCCL all-reduce instead.  ``timed_out()`` reports a barrier spin that gave up
+    (a rank that never made the call); check it wherever a silent desynchronisation would matter.
 
     ``overlap=True``: the buffer is exchanged bucket by bucket (the engine's gradient buckets: pairs of mapper layers, final
     long before the mapper backward ends; ``eavqa_set_grad_events``) on a communication stream, each call on at most
