@@ -1001,6 +1001,28 @@ void sum_over_batch_f32(const float* src, int64_t batch_stride, int B, int n, fl
 }
 void fill_zero(void* p, size_t bytes, cudaStream_t s) { CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, s)); }
 
+namespace {
+constexpr int kPrefetchChunk = 8192;
+__global__ void __launch_bounds__(128) prefetch_l2_kernel(const uint8_t* __restrict__ base, size_t bytes) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t off = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * kPrefetchChunk;
+    if (off < bytes) {
+        const size_t left = bytes - off;
+        const uint32_t sz = static_cast<uint32_t>(left < static_cast<size_t>(kPrefetchChunk) ? left : static_cast<size_t>(kPrefetchChunk)) & ~15u;
+        if (sz > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(sz) : "memory");
+    }
+}
+}  // namespace
+
+void prefetch_l2(const void* p, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return;
+    const int threads = static_cast<int>(ceil_div64(static_cast<int64_t>(bytes), kPrefetchChunk));
+    launch_kernel(prefetch_l2_kernel, dim3(ceil_div(threads, 128)), dim3(128), 0, s, static_cast<const uint8_t*>(p), bytes);
+    KERNEL_CHECK();
+    count_launch();
+}
+
 void layernorm_fwd(const float* x, int ld_x, const int* row_index, const float* gamma, const float* beta, bf16* y,
                    int ld_y, float* mean, float* rstd, int M, int d, float eps, cudaStream_t s) {
     EAVQA_CHECK(d % 4 == 0 && d <= 2048 && ld_x % 4 == 0 && ld_y % 4 == 0, "layernorm width must be a multiple of 4 and <= 2048");

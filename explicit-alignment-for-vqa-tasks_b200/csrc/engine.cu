@@ -236,6 +236,15 @@ void Engine::bucket_done(int bucket, cudaStream_t main) {
     CUDA_CHECK(cudaEventRecord(grad_events_[bucket], side_));
 }
 
+cudaEvent_t Engine::next_pf_event() {
+    if (pf_used_ == pf_events_.size()) {
+        cudaEvent_t ev;
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        pf_events_.push_back(ev);
+    }
+    return pf_events_[pf_used_++];
+}
+
 cudaStream_t Engine::fork(cudaStream_t main) {
     if (!side_enabled_ || gemm_profile_active()) return main;
     if (fork_used_ == fork_events_.size()) {
@@ -266,6 +275,8 @@ Engine::~Engine() {
     for (void* p : owned_) cudaFree(p);
     if (host_flags_) cudaFreeHost(host_flags_);
     if (dec_graph_) cudaGraphExecDestroy(dec_graph_);
+    for (cudaEvent_t ev : pf_events_) cudaEventDestroy(ev);
+    if (pf_stream_) cudaStreamDestroy(pf_stream_);
     if (dec_stream_) cudaStreamDestroy(dec_stream_);
 }
 
@@ -904,14 +915,37 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
                         validD + T0 + step, Tmax, part_val, part_idx, arrivals, s);
         }
     }
+    // KV prefetch, opt-in (EAVQA_KV_PREFETCH=1): after layer l's attention a second stream pulls layer l + 1's KV history
+    // (2 x B x H x Tmax x 128 B, one contiguous region) into L2 with cp.async.bulk.prefetch.L2 while the four projection GEMMs
+    // and the glue of layer l run, so that the next attention would stream from L2 instead of HBM.  Measured on B200
+    // (configs[3], parity-green): 24.2 - 24.5 ms per 128-answer batch against 23.3 - 23.4 without -- the projection GEMMs are
+    // chains of dependent memory round trips, and 80 MB of prefetch traffic per layer lengthens every one of them by more
+    // than the attention gains.  Off by default.
+    static const bool kv_prefetch = [] { const char* e = getenv("EAVQA_KV_PREFETCH"); return e != nullptr && e[0] == '1'; }();
+    const bool use_prefetch = kv_prefetch && kv_layer * sizeof(bf16) <= (96u << 20);      // one layer's history must fit in L2
     auto decode_loop = [&](cudaStream_t st) {
+        if (use_prefetch && pf_stream_ == nullptr) CUDA_CHECK(cudaStreamCreateWithFlags(&pf_stream_, cudaStreamNonBlocking));
+        pf_used_ = 0;
+        cudaEvent_t pf_done = nullptr;                         // the prefetch of the layer about to run has been issued
         for (int step = 1; step < max_new; ++step) {
             const int pos = T0 + step - 1;
             decode_residual_ln(x_a, nullptr, nullptr, layers_[0].ln1_g, layers_[0].ln1_b, u, B, d, 1e-5f, acc_qkv, 3 * d, st);
             for (int l = 0; l < L; ++l) {
                 const LmLayer& w = layers_[l];
                 gemm_decode(u, d, w.w_qkv_t, d, B, 3 * d, d, acc_qkv, st);
+                if (pf_done != nullptr) {
+                    CUDA_CHECK(cudaStreamWaitEvent(st, pf_done, 0));
+                    pf_done = nullptr;
+                }
                 lm_attention_decode_acc(acc_qkv, w.b_qkv, kv + kv_layer * l, validD, Tmax, att, acc_o, B, H_, pos, Tmax, st);
+                if (use_prefetch && !(step == max_new - 1 && l == L - 1)) {
+                    cudaEvent_t att_done = next_pf_event();
+                    CUDA_CHECK(cudaEventRecord(att_done, st));
+                    CUDA_CHECK(cudaStreamWaitEvent(pf_stream_, att_done, 0));
+                    prefetch_l2(kv + kv_layer * ((l + 1) % L), kv_layer * sizeof(bf16), pf_stream_);
+                    pf_done = next_pf_event();
+                    CUDA_CHECK(cudaEventRecord(pf_done, pf_stream_));
+                }
                 gemm_decode(att, d, w.w_o_t, d, B, d, d, acc_o, st);
                 decode_residual_ln(x_a, acc_o, w.b_o, w.ln2_g, w.ln2_b, u, B, d, 1e-5f, acc_pr, d, st);
                 {   // c_fc has 4d / 64 = 64+ tiles of its own: unsplit with the fused bias + gelu epilogue beats split-K plus a
@@ -928,6 +962,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
             }
             head_and_pick(step, st);
         }
+        if (pf_done != nullptr) CUDA_CHECK(cudaStreamWaitEvent(st, pf_done, 0));      // the second stream rejoins
     };
     if (!use_chain && max_new > 1) {
         // The decode loop replayed as ONE CUDA graph (EAVQA_DECODE_GRAPH=0 turns it off; measured 24.46 -> 24.08 ms per
@@ -941,6 +976,7 @@ void Engine::generate(int B, int Tt, int n_images, const float* clip, const int6
         DecodeGraphKey key;
         key.B = B; key.T0 = T0; key.max_new = max_new; key.has_eos = has_eos; key.want_top = top_logit != nullptr;
         key.want_lp = token_logprob != nullptr; key.pad_id = pad_id; key.eos_id = eos_id; key.arena_base = arena_.base();
+        key.prefetch = use_prefetch ? 1 : 0;
         if (!want_graph || !(key == dec_seen_)) {
             dec_seen_ = key;
             decode_loop(s);

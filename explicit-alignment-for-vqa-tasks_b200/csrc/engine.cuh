@@ -113,18 +113,24 @@ private:
     // The single-token steps of generate() as a CUDA graph (on unless EAVQA_DECODE_GRAPH=0): the ~1500 launches of steps 1..max_new-1
     // are captured once per (shape, arena placement) on an engine-owned stream and replayed with one cudaGraphLaunch.
     struct DecodeGraphKey {
-        int B = 0, T0 = 0, max_new = 0, has_eos = 0, want_top = 0, want_lp = 0;
+        int B = 0, T0 = 0, max_new = 0, has_eos = 0, want_top = 0, want_lp = 0, prefetch = 0;
         int64_t pad_id = 0, eos_id = 0;
         const void* arena_base = nullptr;
         bool operator==(const DecodeGraphKey& o) const {
             return B == o.B && T0 == o.T0 && max_new == o.max_new && has_eos == o.has_eos && want_top == o.want_top && want_lp == o.want_lp &&
-                   pad_id == o.pad_id && eos_id == o.eos_id && arena_base == o.arena_base;
+                   pad_id == o.pad_id && eos_id == o.eos_id && arena_base == o.arena_base && prefetch == o.prefetch;
         }
     };
     DecodeGraphKey dec_key_, dec_seen_;
     cudaGraphExec_t dec_graph_ = nullptr;
     int dec_graph_launches_ = 0;         // kernels inside the captured graph (for eavqa_launch_count)
     cudaStream_t dec_stream_ = nullptr;
+    // single-token steps: the NEXT layer's KV history is pulled into L2 on a second stream while the current layer's
+    // projection GEMMs (latency-bound, HBM nearly idle) run
+    cudaStream_t pf_stream_ = nullptr;
+    std::vector<cudaEvent_t> pf_events_;
+    size_t pf_used_ = 0;
+    cudaEvent_t next_pf_event();
 };
 
 }  // namespace eavqa

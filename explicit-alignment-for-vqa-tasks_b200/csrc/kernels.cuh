@@ -38,6 +38,8 @@ void broadcast_rows_f32(const float* src, int rows, int d, float* dst, int64_t b
 // out[c] (+)= sum_b src[b*batch_stride + c]   (prefix_const gradient), c < n
 void sum_over_batch_f32(const float* src, int64_t batch_stride, int B, int n, float* out, cudaStream_t s);
 void fill_zero(void* p, size_t bytes, cudaStream_t s);
+// hint: pull [p, p + bytes) into L2 (cp.async.bulk.prefetch.L2, fire-and-forget; p 16-byte aligned)
+void prefetch_l2(const void* p, size_t bytes, cudaStream_t s);
 
 // ---------------------------------------------------------------- LayerNorm (elementwise.cu)
 // y = LN(x[row]) * gamma + beta, bf16 out; x row = row_index ? row_index[m] : m.  Saves mean / rstd (optional).
